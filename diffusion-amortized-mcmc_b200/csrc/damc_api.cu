@@ -1,0 +1,156 @@
+// damc_api.cu -- extern "C" entry points of libdamc_b200 (declared in include/damc.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "damc_common.cuh"
+#include "damc_internal.h"
+
+namespace damc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision, cudaStream_t stream);
+int dz_splits(int B);
+
+static int check_sm100() {
+  int dev = 0, major = 0;
+  DAMC_CUDA(cudaGetDevice(&dev));
+  DAMC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "libdamc_b200 is built for sm_100a only (device has compute capability %d.x)", major);
+  return DAMC_OK;
+}
+
+}  // namespace damc
+
+using namespace damc;
+
+extern "C" {
+
+int damc_version(void) { return 100; }
+const char* damc_last_error(void) { return g_err; }
+
+int damc_free(damc_handle* h) {
+  delete h;
+  return DAMC_OK;
+}
+
+int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* W3, const float* b3, float negative_slope, void* stream) {
+  if (!out || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) DAMC_FAIL(DAMC_ERR_INVALID, "damc_pack_mlp: null argument");
+  if (nz < 1 || nz > 128 || ndf < 2 || ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "damc_pack_mlp: supported 1<=nz<=128, 2<=ndf<=256 (nz=%d ndf=%d)", nz, ndf);
+  DAMC_TRY(check_sm100());
+  cudaStream_t s = (cudaStream_t)stream;
+  MlpPack* m = new MlpPack();
+  m->kind = H_MLP; m->nz = nz; m->ndf = ndf; m->slope = negative_slope;
+  const size_t n = (size_t)ndf * nz + ndf + (size_t)ndf * ndf + ndf + ndf + 1;
+  if (cudaMalloc(&m->slab, n * sizeof(float)) != cudaSuccess) { delete m; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_mlp: cudaMalloc failed"); }
+  float* p = m->slab;
+  m->W1 = p; p += (size_t)ndf * nz;
+  m->b1 = p; p += ndf;
+  m->W2 = p; p += (size_t)ndf * ndf;
+  m->b2 = p; p += ndf;
+  m->w3 = p; p += ndf;
+  m->b3 = p;
+  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+  cudaMemcpyAsync(m->W1, W1, sizeof(float) * ndf * nz, k, s);
+  cudaMemcpyAsync(m->b1, b1, sizeof(float) * ndf, k, s);
+  cudaMemcpyAsync(m->W2, W2, sizeof(float) * ndf * ndf, k, s);
+  cudaMemcpyAsync(m->b2, b2, sizeof(float) * ndf, k, s);
+  cudaMemcpyAsync(m->w3, W3, sizeof(float) * ndf, k, s);
+  cudaMemcpyAsync(m->b3, b3, sizeof(float), k, s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete m; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_mlp: copy failed: %s", cudaGetErrorString(e)); }
+  *out = m;
+  return DAMC_OK;
+}
+
+int damc_pack_generator(damc_handle** out, int nlayers, const damc_convt_layer* host_layers, float negative_slope,
+                        int precision, void* stream) {
+  if (!out || !host_layers) DAMC_FAIL(DAMC_ERR_INVALID, "damc_pack_generator: null argument");
+  DAMC_TRY(check_sm100());
+  GenPack* g = new GenPack();
+  const int r = build_generator(g, nlayers, host_layers, negative_slope, precision, (cudaStream_t)stream);
+  if (r != DAMC_OK) { delete g; return r; }
+  *out = g;
+  return DAMC_OK;
+}
+
+int damc_generator_shape(const damc_handle* gen, int* nz, int* nc, int* height, int* width) {
+  if (!gen || gen->kind != H_GEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_generator_shape: not a generator handle");
+  const GenPack* g = static_cast<const GenPack*>(gen);
+  if (nz) *nz = g->nz;
+  if (nc) *nc = g->nc;
+  if (height) *height = g->H;
+  if (width) *width = g->W;
+  return DAMC_OK;
+}
+
+size_t damc_generator_workspace_bytes(const damc_handle* gen, int B) {
+  if (!gen || gen->kind != H_GEN || B <= 0) return 0;
+  GenWorkspace ws;
+  plan_workspace(static_cast<const GenPack*>(gen), B, nullptr, &ws);
+  return ws.bytes;
+}
+
+int damc_generator_forward(const damc_handle* gen, const float* z, float* x_hat, int B, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!gen || gen->kind != H_GEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_generator_forward: not a generator handle");
+  if (!z || !x_hat || B <= 0) DAMC_FAIL(DAMC_ERR_INVALID, "damc_generator_forward: bad arguments");
+  const GenPack* g = static_cast<const GenPack*>(gen);
+  GenWorkspace ws;
+  plan_workspace(g, B, workspace, &ws);
+  if (!workspace || workspace_bytes < ws.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  return generator_forward(g, ws, z, B, nullptr, 1.0f, x_hat, nullptr, (cudaStream_t)stream);
+}
+
+int damc_prior_langevin(const damc_handle* ebm, float* z, int B, int K, float step_size, int with_noise,
+                        const float* noise, uint64_t seed, uint64_t chain0, uint64_t step0, float* trace,
+                        void* stream) {
+  if (!ebm || ebm->kind != H_MLP) DAMC_FAIL(DAMC_ERR_INVALID, "damc_prior_langevin: not an EBM handle");
+  if (!z) DAMC_FAIL(DAMC_ERR_INVALID, "damc_prior_langevin: null z");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K == 0) return DAMC_OK;
+  if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 2 * K, s));
+  return launch_ebm_langevin(static_cast<const MlpPack*>(ebm), z, B, K, step_size, with_noise, noise, seed, chain0,
+                             step0, trace, 2, nullptr, 0, 0, 0, s);
+}
+
+int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, float* z, const float* x, int B, int K,
+                            float step_size, float sigma, int with_noise, const float* noise, uint64_t seed,
+                            uint64_t chain0, uint64_t step0, float* trace, float* x_hat_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (!gen || gen->kind != H_GEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_langevin: not a generator handle");
+  if (ebm && ebm->kind != H_MLP) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_langevin: not an EBM handle");
+  if (!z || !x || B <= 0 || K < 0) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_langevin: bad arguments");
+  if (!(sigma > 0.f)) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_langevin: sigma must be > 0");
+  const GenPack* g = static_cast<const GenPack*>(gen);
+  const MlpPack* m = static_cast<const MlpPack*>(ebm);
+  if (m && m->nz != g->nz) DAMC_FAIL(DAMC_ERR_INVALID, "EBM nz %d != generator nz %d", m->nz, g->nz);
+  cudaStream_t s = (cudaStream_t)stream;
+  GenWorkspace ws;
+  plan_workspace(g, B, workspace, &ws);
+  if (!workspace || workspace_bytes < ws.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  if (K == 0) return DAMC_OK;
+  const GenLayer& last = g->layers[g->nlayers - 1];
+  // unused im2col slots (image border taps, channel padding) must read as zero; live slots are rewritten every step
+  DAMC_CUDA(cudaMemsetAsync(ws.gcol, 0, elem_size(g->precision) * (size_t)B * last.Hin * last.Win * 64, s));
+  if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 4 * K, s));
+  const int S = dz_splits(B);
+  for (int i = 0; i < K; ++i) {
+    float* tr = trace ? trace + 4 * (size_t)i : nullptr;
+    DAMC_TRY(generator_forward(g, ws, z, B, x, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, s));
+    DAMC_TRY(generator_dgrad(g, ws, B, s));
+    DAMC_TRY(launch_ebm_langevin(m, z, B, 1, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr,
+                                 seed, chain0, step0 + (uint64_t)i, tr, 4, ws.dz_part, S, g->nz_p, g->nz, s));
+  }
+  return DAMC_OK;
+}
+
+}  // extern "C"

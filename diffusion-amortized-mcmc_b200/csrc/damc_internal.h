@@ -1,0 +1,117 @@
+// damc_internal.h -- handle structs and cross-file launch prototypes (not part of the C ABI).
+#pragma once
+#include "damc_common.cuh"
+
+struct damc_handle {
+  int kind;
+  virtual ~damc_handle() {}
+};
+
+namespace damc {
+
+// ---- EBM MLP (weights kept in the reference's Linear layouts; the persistent kernel re-tiles them into smem) -------
+struct MlpPack : damc_handle {
+  int nz = 0, ndf = 0;
+  float slope = 0.2f;
+  float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  float* slab = nullptr;
+  ~MlpPack() override { if (slab) cudaFree(slab); }
+};
+
+int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, int with_noise, const float* noise,
+                        uint64_t seed, uint64_t chain0, uint64_t step0, float* trace, int trace_stride,
+                        const float* gpart, int nsplit, int gstride, int nz_if_no_ebm, cudaStream_t stream);
+
+// ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
+// Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]
+// with m = (b,y,x) on an Hm x Wm grid, and A_t[m,:] = src[plane_t][b, y+dy_t, x+dx_t, :] (zero outside the grid).
+enum LayerType { L_FIRST = 0, L_UP = 1, L_SAME = 2 };  // 1x1->kxk (s1,p0) | k4,s2,p1 | k3,s1,p1
+enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3 };
+
+struct Tap { signed char plane, dy, dx, pad; };
+
+struct Epilogue {
+  int kind;
+  void* out;            // activation / gradient tensor (element type T)
+  const float* bias;    // [bias_mod] or null
+  int bias_mod;
+  long long o_b, o_y, o_x;  // EPI_FWD_ACT: out offset = b*o_b + (y*sy+py)*o_y + (x*sx+px)*o_x + n
+  int sy, sx, py, px;
+  float slope;
+  // EPI_DGRAD_MASK: sign source = activation of the producing layer, NHWC on the M grid, C = N
+  const void* act;
+  int planar_out;       // 1: scatter (y,x) into 4 parity planes [4][B][Hm/2][Wm/2][N]; 0: flat [M][N]
+  // EPI_FWD_LAST
+  const float* x;       // [B,nc,Ho,Wo] or null (forward only)
+  float* xhat;          // [B,nc,Ho,Wo] or null
+  float inv_sigma2;
+  float* loss;          // null or scalar accumulator: sum (xhat-x)^2 * inv_sigma2/2
+  void* gcol;           // im2col'd dL/dh_last for the last layer's dgrad: [B*Hi*Wi][64], slot (kh*k+kw)*4 + c
+  int nc, k, stride, padding, Hi, Wi, Ho, Wo;
+  // EPI_DGRAD_Z
+  int nz_out;           // row stride of the fp32 partial-sum output [split][B][nz_out]
+};
+
+struct GemmPlan {
+  const void* A;            // element type T
+  long long plane_stride;   // elements between source planes
+  int B, Hm, Wm, Cs;        // M grid and K per tap (multiple of 64)
+  int ntaps;
+  Tap taps[16];
+  const void* W;            // SIMT: [ntaps*Cs][Np] fp32/bf16 (N contiguous);  TC: [ntaps][Np][Cs] bf16 (K contiguous)
+  int N, Np;                // logical / padded (multiple of 16) output columns
+  int ksplit;               // >1: grid.z splits the K loop (EPI_DGRAD_Z only)
+  Epilogue epi;
+};
+
+struct GenLayer {
+  int type, cin, cout, k, stride, pad, Hin, Win, Hout, Wout;
+  int cin_p;  // cin padded to a multiple of 64 (first layer: nz)
+  const float* bias = nullptr;           // device copy
+  // packed weights: fwd (per parity class for L_UP: 4, else 1) and dgrad
+  void* w_fwd[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* w_dgrad = nullptr;
+  int n_fwd = 0, np_fwd = 0;    // N / padded N of the forward GEMM
+  int n_dg = 0, np_dg = 0;      // N / padded N of the dgrad GEMM
+};
+
+struct GenPack : damc_handle {
+  int precision = DAMC_PREC_FP32;
+  int nlayers = 0, nz = 0, nz_p = 0, nc = 0, H = 0, W = 0;
+  float slope = 0.2f;
+  std::vector<GenLayer> layers;
+  std::vector<void*> allocs;
+  int dz_splits = 1;
+  ~GenPack() override { for (void* p : allocs) cudaFree(p); }
+};
+
+struct GenWorkspace {   // carved out of the caller's workspace for a given B
+  void* zin;                 // [B][nz_p]          T
+  std::vector<void*> act;    // a_1..a_{L-1}       T (NHWC)
+  std::vector<void*> grad;   // g_1..g_{L-1}       T (planar for L_UP producers, flat for L_FIRST)
+  void* gcol;                // [B*Hi*Wi][64]      T
+  float* dz_part;            // [splits][B][nz_p]  fp32
+  size_t bytes;
+};
+
+size_t elem_size(int precision);
+int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws);
+
+// SIMT implicit GEMM (fp32 or bf16 storage, fp32 accumulate) -- gen_simt.cu
+int launch_gemm_simt(const GemmPlan& p, int precision, cudaStream_t stream);
+// tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate) -- gen_tc.cu
+int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream);
+int tc_available();
+
+// weight packing -- gen_pack.cu
+enum PackMode { PK_FIRST_FWD, PK_FIRST_DGRAD, PK_UP_FWD, PK_UP_DGRAD, PK_SAME_FWD, PK_LAST_DGRAD_COL };
+int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int pad, int mode, int cls, int ntaps,
+                      int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream);
+int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int precision, cudaStream_t stream);
+
+// generator driver -- gen_driver.cu
+int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
+                      float* xhat, float* loss, cudaStream_t stream);
+int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream);
+
+}  // namespace damc

@@ -1,0 +1,365 @@
+// ebm_langevin.cu -- persistent on-device Langevin chain loop with the EBM-prior MLP resident in shared memory.
+//
+// Replaces sample_langevin_prior_z (reference workspace/src/MCMC.py:27-46) and the per-step "E + prior + update"
+// tail of sample_langevin_post_z_with_prior (:57-64).  One launch runs all K steps:
+//     h1 = W1 z + b1 ; h2 = W2 lrelu(h1) + b2 ; E = w3.lrelu(h2) + b3                  (diffusion_net.py:212-223)
+//     gE = W1^T( n1 * W2^T( n2 * w3 ) ),  n = 1 | slope                                  (analytic backward)
+//     z <- z - s^2/2 (gE [+ gG] + z) + s * eps                                           (MCMC.py:36-38 / :62-64)
+//
+// B200 layout: fp32 weights are 4*(nz*ndf + ndf*ndf) = 262 KB at nz=128, ndf=200 -- more than one SM's 227 KB -- so a
+// 2-CTA thread-block cluster owns a tile of CH chains and splits the HIDDEN units: CTA r keeps rows J_r of W1 and
+// columns J_r of W2 (131 KB) for the whole kernel.  Two DSMEM exchanges per step (layer-2 partial sums, dz partial
+// sums); both CTAs then hold identical z (fp add is commutative, so the two sums are bit-identical).  No HBM traffic
+// inside the loop except optional injected noise; z is read once and written once.
+#include <cooperative_groups.h>
+
+#include "damc_common.cuh"
+#include "damc_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace damc {
+
+static __host__ __device__ inline int pad_stride(int n) {  // >= n, == 4 (mod 32): conflict-free LDS.128 across rows
+  int s = (n + 3) & ~3;
+  while ((s & 31) != 4) s += 4;
+  return s;
+}
+
+struct EbmSmemPlan {
+  int HJ, HJP, NZP, S1, S2;
+  size_t oW1, oW2, ob1, ob2, ow3, oz, oa1, op, opp, od2, ot, od1, og, ogp, ored, total;
+};
+
+template <int CH>
+static __host__ __device__ inline EbmSmemPlan ebm_plan(int nz, int ndf) {
+  EbmSmemPlan p;
+  p.HJ = (ndf + 1) / 2;
+  p.HJP = (p.HJ + 3) & ~3;
+  p.NZP = (nz + 3) & ~3;
+  p.S1 = pad_stride(p.NZP);
+  p.S2 = pad_stride(p.HJP);
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+  p.oW1 = take((size_t)p.HJ * p.S1);
+  p.oW2 = take((size_t)ndf * p.S2);
+  p.ob1 = take(p.HJ);
+  p.ob2 = take(ndf);
+  p.ow3 = take(ndf);
+  p.oz = take((size_t)CH * p.NZP);
+  p.oa1 = take((size_t)CH * p.HJP);
+  p.op = take((size_t)CH * ndf);
+  p.opp = take((size_t)CH * ndf);
+  p.od2 = take((size_t)ndf * CH);
+  p.ot = take((size_t)2 * p.HJ * CH);
+  p.od1 = take((size_t)p.HJ * CH);
+  p.og = take((size_t)2 * CH * p.NZP);
+  p.ogp = take((size_t)CH * p.NZP);
+  p.ored = take(4 * CH);
+  p.total = o * sizeof(float);
+  return p;
+}
+
+struct EbmArgs {
+  const float *W1, *b1, *W2, *b2, *w3, *b3;  // PyTorch Linear layouts, fp32, device
+  int nz, ndf;
+  float slope;
+  float* z;  // [B,nz] in/out
+  int B, K;
+  float step;
+  int with_noise;
+  const float* noise;  // [K,B,nz] or null
+  uint64_t seed, chain0, step0;
+  float* trace;      // null or [K, trace_stride]
+  int trace_stride;  // 2 (prior: en, z_norm) or 4 (posterior: en, llhd(other kernel), z_n, mean grad)
+  const float* gpart;  // null or [nsplit][B][gstride] generator dz partial sums
+  int nsplit, gstride;
+  float inv_count;  // 1/(B*nz) for mean(grad)
+  int use_ebm;      // 0: skip the MLP (toy-style target), update only
+};
+
+template <int CH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) ebm_langevin_kernel(const EbmArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int nz = a.nz, ndf = a.ndf;
+  const EbmSmemPlan P = ebm_plan<CH>(nz, ndf);
+  const int HJ = P.HJ, HJP = P.HJP, NZP = P.NZP, S1 = P.S1, S2 = P.S2;
+  const int j0 = rank * HJ;                      // first hidden unit owned by this CTA
+  const int hj = max(0, min(HJ, ndf - j0));      // number owned (rank 1 may own fewer when ndf is odd)
+  float* sW1 = smem + P.oW1;  // [HJ][S1]   rows j0.. of W1
+  float* sW2 = smem + P.oW2;  // [ndf][S2]  columns j0.. of W2
+  float* sb1 = smem + P.ob1;
+  float* sb2 = smem + P.ob2;
+  float* sw3 = smem + P.ow3;
+  float* sz = smem + P.oz;    // [CH][NZP]
+  float* sa1 = smem + P.oa1;  // [CH][HJP]
+  float* sp = smem + P.op;    // [CH][ndf]  own layer-2 partial
+  float* spp = smem + P.opp;  // [CH][ndf]  peer's partial (written by the peer through DSMEM)
+  float* sd2 = smem + P.od2;  // [ndf][CH]
+  float* st = smem + P.ot;    // [2][HJ][CH]
+  float* sd1 = smem + P.od1;  // [HJ][CH]
+  float* sg = smem + P.og;    // [2][CH][NZP]
+  float* sgp = smem + P.ogp;  // [CH][NZP]  peer's dz partial
+  float* sred = smem + P.ored;
+  float* peer_spp = cluster.map_shared_rank(spp, rank ^ 1);
+  float* peer_sgp = cluster.map_shared_rank(sgp, rank ^ 1);
+
+  const int cl = blockIdx.x >> 1;
+  const int c0 = cl * CH;
+  const int nvalid = min(CH, a.B - c0);
+
+  // ---- one-time: weights -> smem (zero padded), z tile -> smem ---------------------------------------------------
+  if (a.use_ebm) {
+    for (int i = tid; i < HJ * S1; i += blockDim.x) {
+      const int r = i / S1, c = i - r * S1;
+      sW1[i] = (r < hj && c < nz) ? a.W1[(size_t)(j0 + r) * nz + c] : 0.f;
+    }
+    for (int i = tid; i < ndf * S2; i += blockDim.x) {
+      const int r = i / S2, c = i - r * S2;
+      sW2[i] = (c < hj) ? a.W2[(size_t)r * ndf + j0 + c] : 0.f;
+    }
+    for (int i = tid; i < HJ; i += blockDim.x) sb1[i] = i < hj ? a.b1[j0 + i] : 0.f;
+    for (int i = tid; i < ndf; i += blockDim.x) { sb2[i] = a.b2[i]; sw3[i] = a.w3[i]; }
+    for (int i = tid; i < CH * HJP; i += blockDim.x) sa1[i] = 0.f;
+  }
+  for (int i = tid; i < CH * NZP; i += blockDim.x) {
+    const int c = i / NZP, k = i - c * NZP;
+    sz[i] = (c < nvalid && k < nz) ? a.z[(size_t)(c0 + c) * nz + k] : 0.f;
+  }
+  const float b3 = a.use_ebm ? a.b3[0] : 0.f;
+  const float slope = a.slope;
+  const float half_s2 = 0.5f * a.step * a.step;
+  cluster.sync();
+
+  for (int it = 0; it < a.K; ++it) {
+    if (a.trace != nullptr) {
+      if (tid < 4 * CH) sred[tid] = 0.f;
+      __syncthreads();
+    }
+    if (a.use_ebm) {
+      // ---- phase 1: h1 / a1 for owned hidden units (thread = unit x half of the chains) --------------------------
+      if (tid < 2 * hj) {
+        const int jl = tid % hj, cg0 = (tid / hj) * (CH / 2);
+        float acc[CH / 2];
+#pragma unroll
+        for (int c = 0; c < CH / 2; ++c) acc[c] = 0.f;
+        const float4* w = reinterpret_cast<const float4*>(sW1 + (size_t)jl * S1);
+        for (int i = 0; i < NZP / 4; ++i) {
+          const float4 wv = w[i];
+#pragma unroll
+          for (int c = 0; c < CH / 2; ++c) {
+            const float4 zv = reinterpret_cast<const float4*>(sz + (size_t)(cg0 + c) * NZP)[i];
+            acc[c] = fmaf(wv.x, zv.x, acc[c]);
+            acc[c] = fmaf(wv.y, zv.y, acc[c]);
+            acc[c] = fmaf(wv.z, zv.z, acc[c]);
+            acc[c] = fmaf(wv.w, zv.w, acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH / 2; ++c) {
+          const float h = acc[c] + sb1[jl];
+          sa1[(size_t)(cg0 + c) * HJP + jl] = h > 0.f ? h : slope * h;
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: layer-2 partial sums over owned units, for every output unit (thread = output unit) ---------
+      if (tid < ndf) {
+        float acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+        const float4* w = reinterpret_cast<const float4*>(sW2 + (size_t)tid * S2);
+        for (int i = 0; i < HJP / 4; ++i) {
+          const float4 wv = w[i];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const float4 av = reinterpret_cast<const float4*>(sa1 + (size_t)c * HJP)[i];
+            acc[c] = fmaf(wv.x, av.x, acc[c]);
+            acc[c] = fmaf(wv.y, av.y, acc[c]);
+            acc[c] = fmaf(wv.z, av.z, acc[c]);
+            acc[c] = fmaf(wv.w, av.w, acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          sp[c * ndf + tid] = acc[c];
+          peer_spp[c * ndf + tid] = acc[c];  // DSMEM store
+        }
+      }
+      cluster.sync();
+      // ---- h2, E, d2 = n2 * w3 (thread = output unit; both CTAs compute the same values) --------------------------
+      if (tid < ndf) {
+        const float w3 = sw3[tid], bb = sb2[tid];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const float h = (sp[c * ndf + tid] + spp[c * ndf + tid]) + bb;
+          sd2[tid * CH + c] = (h > 0.f ? 1.f : slope) * w3;
+          if (a.trace != nullptr && rank == 0 && c < nvalid) atomicAdd(&sred[c], w3 * (h > 0.f ? h : slope * h));
+        }
+      }
+      __syncthreads();
+      // ---- phase 3: t = W2[:,J]^T d2 over two halves of the output units (thread = owned unit x half) ------------
+      if (tid < 2 * hj) {
+        const int il = tid % hj, hf = tid / hj;
+        const int jb = hf * ((ndf + 1) / 2), je = min(ndf, jb + (ndf + 1) / 2);
+        float acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+        for (int j = jb; j < je; ++j) {
+          const float wv = sW2[(size_t)j * S2 + il];
+#pragma unroll
+          for (int c4 = 0; c4 < CH / 4; ++c4) {
+            const float4 dv = reinterpret_cast<const float4*>(sd2 + j * CH)[c4];
+            acc[c4 * 4 + 0] = fmaf(wv, dv.x, acc[c4 * 4 + 0]);
+            acc[c4 * 4 + 1] = fmaf(wv, dv.y, acc[c4 * 4 + 1]);
+            acc[c4 * 4 + 2] = fmaf(wv, dv.z, acc[c4 * 4 + 2]);
+            acc[c4 * 4 + 3] = fmaf(wv, dv.w, acc[c4 * 4 + 3]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) st[((size_t)hf * HJ + il) * CH + c] = acc[c];
+      }
+      __syncthreads();
+      for (int i = tid; i < hj * CH; i += blockDim.x) {
+        const int il = i / CH, c = i - il * CH;
+        const float tv = st[i] + st[(size_t)HJ * CH + i];
+        sd1[i] = (sa1[(size_t)c * HJP + il] > 0.f ? 1.f : slope) * tv;
+      }
+      __syncthreads();
+      // ---- phase 4: dz partial = W1[J,:]^T d1 (thread = latent dim x half of the owned units) ---------------------
+      if (tid < 2 * NZP) {
+        const int k = tid % NZP, hf = tid / NZP;
+        const int ib = hf * ((hj + 1) / 2), ie = min(hj, ib + (hj + 1) / 2);
+        float acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+        for (int i = ib; i < ie; ++i) {
+          const float wv = sW1[(size_t)i * S1 + k];
+#pragma unroll
+          for (int c4 = 0; c4 < CH / 4; ++c4) {
+            const float4 dv = reinterpret_cast<const float4*>(sd1 + i * CH)[c4];
+            acc[c4 * 4 + 0] = fmaf(wv, dv.x, acc[c4 * 4 + 0]);
+            acc[c4 * 4 + 1] = fmaf(wv, dv.y, acc[c4 * 4 + 1]);
+            acc[c4 * 4 + 2] = fmaf(wv, dv.z, acc[c4 * 4 + 2]);
+            acc[c4 * 4 + 3] = fmaf(wv, dv.w, acc[c4 * 4 + 3]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) sg[((size_t)hf * CH + c) * NZP + k] = acc[c];
+      }
+      __syncthreads();
+      for (int i = tid; i < CH * NZP; i += blockDim.x) {
+        const float v = sg[i] + sg[(size_t)CH * NZP + i];
+        sg[i] = v;
+        peer_sgp[i] = v;  // DSMEM store
+      }
+      cluster.sync();
+    }
+    // ---- phase 5: fused update  z <- z - s^2/2 (gE + gG + z) + s eps   (thread = quad of latent dims) -------------
+    for (int qb = 0; qb < CH * NZP / 4; qb += blockDim.x) {  // uniform trip count: warp_sum below needs all lanes
+      const int q = min(qb + tid, CH * NZP / 4 - 1);
+      const bool mine = qb + tid < CH * NZP / 4;
+      const int c = q / (NZP / 4), k4 = (q - c * (NZP / 4)) * 4;
+      const bool live = mine && c < nvalid;
+      const uint64_t chain = a.chain0 + (uint64_t)(c0 + c);
+      float4 zv = reinterpret_cast<float4*>(sz + (size_t)c * NZP)[k4 >> 2];
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.use_ebm) {
+        const float4 g0 = reinterpret_cast<const float4*>(sg + (size_t)c * NZP)[k4 >> 2];
+        const float4 g1 = reinterpret_cast<const float4*>(sgp + (size_t)c * NZP)[k4 >> 2];
+        g[0] = g0.x + g1.x; g[1] = g0.y + g1.y; g[2] = g0.z + g1.z; g[3] = g0.w + g1.w;
+      }
+      float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        if (a.gpart != nullptr) {
+          for (int s = 0; s < a.nsplit; ++s) {
+            const float* gp = a.gpart + ((size_t)s * a.B + (c0 + c)) * a.gstride + k4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k4 + e < nz) g[e] += gp[e];
+          }
+        }
+        if (a.with_noise) {
+          if (a.noise != nullptr) {
+            const float* np = a.noise + ((size_t)it * a.B + (c0 + c)) * nz + k4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k4 + e < nz) nrm[e] = np[e];
+          } else {
+            philox_normal4(a.seed, chain, a.step0 + (uint64_t)it, (uint32_t)(k4 >> 2), nrm);
+          }
+        }
+      }
+      float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+      float zsq = 0.f, gsum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = live && (k4 + e < nz);
+        const float grad = g[e] + zz[e];
+        zsq += ok ? zz[e] * zz[e] : 0.f;
+        gsum += ok ? grad : 0.f;
+        zz[e] = ok ? (zz[e] - half_s2 * grad + a.step * nrm[e]) : 0.f;
+      }
+      if (mine) reinterpret_cast<float4*>(sz + (size_t)c * NZP)[k4 >> 2] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      if (a.trace != nullptr && rank == 0) {
+        zsq = warp_sum(zsq);
+        gsum = warp_sum(gsum);
+        if ((tid & 31) == 0) { atomicAdd(&sred[CH], zsq); atomicAdd(&sred[CH + 1], gsum); }
+      }
+    }
+    __syncthreads();
+    if (a.trace != nullptr && rank == 0 && tid == 0) {
+      float en = 0.f;
+      for (int c = 0; c < nvalid; ++c) en += sred[c] + b3;
+      float* tr = a.trace + (size_t)it * a.trace_stride;
+      if (a.use_ebm) atomicAdd(&tr[0], en);
+      if (a.trace_stride == 2) {
+        atomicAdd(&tr[1], 0.5f * sred[CH]);
+      } else {
+        atomicAdd(&tr[2], 0.5f * sred[CH]);
+        atomicAdd(&tr[3], sred[CH + 1] * a.inv_count);
+      }
+    }
+    if (a.trace != nullptr) __syncthreads();  // thread 0 has consumed sred before the next iteration re-zeroes it
+  }
+  if (rank == 0) {
+    for (int i = tid; i < CH * NZP; i += blockDim.x) {
+      const int c = i / NZP, k = i - c * NZP;
+      if (c < nvalid && k < nz) a.z[(size_t)(c0 + c) * nz + k] = sz[i];
+    }
+  }
+  cluster.sync();  // keep both CTAs' shared memory alive until all DSMEM traffic has landed
+}
+
+static constexpr int kChains = 8;
+
+int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, int with_noise, const float* noise,
+                        uint64_t seed, uint64_t chain0, uint64_t step0, float* trace, int trace_stride,
+                        const float* gpart, int nsplit, int gstride, int nz_if_no_ebm, cudaStream_t stream) {
+  EbmArgs a{};
+  a.use_ebm = m != nullptr;
+  if (m) {
+    a.W1 = m->W1; a.b1 = m->b1; a.W2 = m->W2; a.b2 = m->b2; a.w3 = m->w3; a.b3 = m->b3;
+    a.nz = m->nz; a.ndf = m->ndf; a.slope = m->slope;
+  } else {
+    a.nz = nz_if_no_ebm; a.ndf = 2; a.slope = 1.f;
+  }
+  if (a.nz < 1 || a.nz > 128) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM Langevin kernel supports 1 <= nz <= 128 (got %d)", a.nz);
+  if (a.ndf < 2 || a.ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM Langevin kernel supports ndf <= 256 (got %d)", a.ndf);
+  if (B <= 0 || K < 0) DAMC_FAIL(DAMC_ERR_INVALID, "B must be > 0 and K >= 0 (B=%d K=%d)", B, K);
+  a.z = z; a.B = B; a.K = K; a.step = step; a.with_noise = with_noise; a.noise = noise;
+  a.seed = seed; a.chain0 = chain0; a.step0 = step0; a.trace = trace; a.trace_stride = trace_stride;
+  a.gpart = gpart; a.nsplit = nsplit; a.gstride = gstride; a.inv_count = 1.0f / ((float)B * (float)a.nz);
+  const EbmSmemPlan P = ebm_plan<kChains>(a.nz, a.ndf);
+  if (P.total > 227 * 1024) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM weights need %zu B of shared memory per CTA", P.total);
+  DAMC_CUDA(cudaFuncSetAttribute(ebm_langevin_kernel<kChains>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)P.total));
+  const int clusters = ceil_div(B, kChains);
+  ebm_langevin_kernel<kChains><<<2 * clusters, 256, P.total, stream>>>(a);
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+}  // namespace damc

@@ -1,0 +1,229 @@
+// gen_driver.cu -- host-side planning for the generator: weight packing, workspace carving and the per-step chain of
+// shifted-window GEMMs (forward G(z), likelihood gradient, backward with respect to z).
+//
+// Replaces, per Langevin step, netG(z) + autograd.grad through netG of sample_langevin_post_z_with_prior (reference
+// workspace/src/MCMC.py:55-60) for the generator families of workspace/src/diffusion_net.py:20-203.
+#include <algorithm>
+
+#include "damc_common.cuh"
+#include "damc_internal.h"
+
+namespace damc {
+
+static int dz_splits_for(int B) {
+  const int mt = ceil_div(B, 128);
+  return std::max(1, std::min(32, 296 / mt));
+}
+
+static int dev_alloc(GenPack* g, void** p, size_t bytes) {
+  DAMC_CUDA(cudaMalloc(p, bytes));
+  g->allocs.push_back(*p);
+  return DAMC_OK;
+}
+
+int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision,
+                    cudaStream_t stream) {
+  if (nlayers < 2 || nlayers > 8) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "generator needs 2..8 ConvTranspose2d layers (got %d)", nlayers);
+  if (precision != DAMC_PREC_FP32 && precision != DAMC_PREC_BF16) DAMC_FAIL(DAMC_ERR_INVALID, "unknown precision %d", precision);
+  g->kind = H_GEN;
+  g->precision = precision;
+  g->nlayers = nlayers;
+  g->slope = slope;
+  g->nz = L[0].cin;
+  g->nz_p = (int)align_up(g->nz, 64);
+  const int cmult = precision == DAMC_PREC_BF16 ? 64 : 16;
+  int H = 1, W = 1;
+  g->layers.resize(nlayers);
+  for (int i = 0; i < nlayers; ++i) {
+    GenLayer& y = g->layers[i];
+    const damc_convt_layer& s = L[i];
+    if (s.weight == nullptr) DAMC_FAIL(DAMC_ERR_INVALID, "layer %d: null weight", i);
+    if (i > 0 && s.cin != L[i - 1].cout) DAMC_FAIL(DAMC_ERR_INVALID, "layer %d: cin %d != previous cout %d", i, s.cin, L[i - 1].cout);
+    y.cin = s.cin; y.cout = s.cout; y.k = s.k; y.stride = s.stride; y.pad = s.pad; y.Hin = H; y.Win = W;
+    if (i == 0) {
+      if (s.stride != 1 || s.pad != 0) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "first layer must be 1x1 -> kxk with stride 1, padding 0");
+      y.type = L_FIRST;
+      y.Hout = y.Wout = s.k;
+    } else if (s.k == 4 && s.stride == 2 && s.pad == 1) {
+      y.type = L_UP;
+      y.Hout = 2 * H; y.Wout = 2 * W;
+    } else if (s.k == 3 && s.stride == 1 && s.pad == 1 && i == nlayers - 1) {
+      y.type = L_SAME;
+      y.Hout = H; y.Wout = W;
+    } else {
+      DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "layer %d: ConvTranspose2d(k=%d,s=%d,p=%d) is not one of the reference's shapes", i, s.k, s.stride, s.pad);
+    }
+    if (i < nlayers - 1 && s.cout % cmult) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "layer %d: %d channels; this precision needs a multiple of %d", i, s.cout, cmult);
+    if (i == nlayers - 1 && (s.cout > 4 || s.k * s.k > 16)) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "last layer: nc <= 4 and k <= 4 supported (nc=%d k=%d)", s.cout, s.k);
+    y.cin_p = i == 0 ? g->nz_p : s.cin;
+    H = y.Hout; W = y.Wout;
+  }
+  g->nc = L[nlayers - 1].cout; g->H = H; g->W = W;
+
+  const size_t es = elem_size(precision);
+  for (int i = 0; i < nlayers; ++i) {
+    GenLayer& y = g->layers[i];
+    const damc_convt_layer& s = L[i];
+    const bool last = i == nlayers - 1;
+    // bias (fp32 device copy; the caller's tensor may be re-used by the optimiser between calls)
+    float* bias = nullptr;
+    DAMC_TRY(dev_alloc(g, (void**)&bias, sizeof(float) * s.cout));
+    if (s.bias) DAMC_CUDA(cudaMemcpyAsync(bias, s.bias, sizeof(float) * s.cout, cudaMemcpyDeviceToDevice, stream));
+    else DAMC_CUDA(cudaMemsetAsync(bias, 0, sizeof(float) * s.cout, stream));
+    y.bias = bias;
+    // forward operands
+    int ntaps, Cs, mode, ncls = 1;
+    if (y.type == L_FIRST) { ntaps = 1; Cs = y.cin_p; mode = PK_FIRST_FWD; y.n_fwd = s.k * s.k * s.cout; }
+    else if (y.type == L_UP) { ntaps = 4; Cs = y.cin; mode = PK_UP_FWD; ncls = 4; y.n_fwd = s.cout; }
+    else { ntaps = 9; Cs = y.cin; mode = PK_SAME_FWD; y.n_fwd = s.cout; }
+    y.np_fwd = (int)align_up(y.n_fwd, 16);
+    for (int c = 0; c < ncls; ++c) {
+      DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
+      DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
+                                 precision, y.w_fwd[c], stream));
+    }
+    // dgrad operands
+    if (last) { ntaps = 1; Cs = 64; mode = PK_LAST_DGRAD_COL; }
+    else if (y.type == L_FIRST) { ntaps = 1; Cs = s.k * s.k * s.cout; mode = PK_FIRST_DGRAD; }
+    else { ntaps = 16; Cs = s.cout; mode = PK_UP_DGRAD; }
+    y.n_dg = s.cin;
+    y.np_dg = (int)align_up(y.n_dg, 16);
+    DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
+    DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 0,
+                               precision, y.w_dgrad, stream));
+  }
+  return DAMC_OK;
+}
+
+int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
+  const size_t es = elem_size(g->precision);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return base ? (void*)((char*)base + r) : nullptr; };
+  const int L = g->nlayers;
+  ws->zin = take(es * (size_t)B * g->nz_p);
+  ws->act.assign(L - 1, nullptr);
+  ws->grad.assign(L - 1, nullptr);
+  for (int l = 0; l < L - 1; ++l) {
+    const GenLayer& y = g->layers[l];
+    const size_t n = (size_t)B * y.Hout * y.Wout * y.cout;
+    ws->act[l] = take(es * n);
+    ws->grad[l] = take(es * n);
+  }
+  const GenLayer& last = g->layers[L - 1];
+  ws->gcol = take(es * (size_t)B * last.Hin * last.Win * 64);
+  ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(B) * B * g->nz_p);
+  ws->bytes = o;
+  return DAMC_OK;
+}
+
+static int run_gemm(const GenPack* g, const GemmPlan& p, cudaStream_t stream) {
+  return launch_gemm_simt(p, g->precision, stream);
+}
+
+static void up_fwd_taps(int cls, GemmPlan& p) {
+  const int py = cls >> 1, px = cls & 1;
+  p.ntaps = 4;
+  for (int ty = 0; ty < 2; ++ty)
+    for (int tx = 0; tx < 2; ++tx) {
+      Tap& t = p.taps[ty * 2 + tx];
+      t.plane = 0;
+      t.dy = (signed char)(py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0));
+      t.dx = (signed char)(px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0));
+    }
+}
+
+int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
+                      float* xhat, float* loss, cudaStream_t stream) {
+  DAMC_TRY(launch_stage_z(z, ws.zin, B, g->nz, g->nz_p, g->precision, stream));
+  const int L = g->nlayers;
+  for (int l = 0; l < L; ++l) {
+    const GenLayer& y = g->layers[l];
+    const bool last = l == L - 1;
+    GemmPlan p{};
+    p.A = l == 0 ? ws.zin : ws.act[l - 1];
+    p.plane_stride = 0;
+    p.B = B; p.Hm = y.Hin; p.Wm = y.Win; p.Cs = y.cin_p;
+    p.N = y.n_fwd; p.Np = y.np_fwd; p.ksplit = 1;
+    Epilogue& e = p.epi;
+    e.slope = g->slope;
+    e.bias = y.bias;
+    e.sy = e.sx = y.type == L_UP ? 2 : 1;
+    if (last) {
+      e.kind = EPI_FWD_LAST;
+      e.x = x; e.xhat = xhat; e.loss = loss; e.gcol = ws.gcol;
+      e.inv_sigma2 = 1.0f / (sigma * sigma);
+      e.nc = y.cout; e.k = y.k; e.stride = y.stride; e.padding = y.pad;
+      e.Hi = y.Hin; e.Wi = y.Win; e.Ho = y.Hout; e.Wo = y.Wout;
+    } else {
+      e.kind = EPI_FWD_ACT;
+      e.out = ws.act[l];
+      e.bias_mod = y.cout;
+      if (y.type == L_FIRST) { e.o_b = (long long)y.n_fwd; e.o_y = 0; e.o_x = 0; }
+      else { e.o_b = (long long)y.Hout * y.Wout * y.cout; e.o_y = (long long)y.Wout * y.cout; e.o_x = y.cout; }
+    }
+    if (y.type == L_FIRST) {
+      p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
+      p.W = y.w_fwd[0];
+      DAMC_TRY(run_gemm(g, p, stream));
+    } else if (y.type == L_UP) {
+      for (int cls = 0; cls < 4; ++cls) {
+        up_fwd_taps(cls, p);
+        p.W = y.w_fwd[cls];
+        e.py = cls >> 1; e.px = cls & 1;
+        DAMC_TRY(run_gemm(g, p, stream));
+      }
+    } else {  // L_SAME: oh = ih - 1 + kh  ->  source row = oh + 1 - kh
+      p.ntaps = 9;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = Tap{0, (signed char)(1 - kh), (signed char)(1 - kw), 0};
+      p.W = y.w_fwd[0];
+      DAMC_TRY(run_gemm(g, p, stream));
+    }
+  }
+  return DAMC_OK;
+}
+
+int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream) {
+  const int L = g->nlayers;
+  for (int l = L - 1; l >= 0; --l) {
+    const GenLayer& y = g->layers[l];
+    GemmPlan p{};
+    p.B = B; p.Hm = y.Hin; p.Wm = y.Win;
+    p.N = y.n_dg; p.Np = y.np_dg; p.ksplit = 1;
+    p.W = y.w_dgrad;
+    Epilogue& e = p.epi;
+    e.slope = g->slope;
+    if (l == L - 1) {  // im2col'd dL/dh written by the forward epilogue
+      p.A = ws.gcol; p.Cs = 64; p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
+    } else if (y.type == L_UP) {  // gin[ih] = sum_kh gout[2 ih - 1 + kh] W[kh]: parity plane (kh+1)&1, shift -1/0/0/+1
+      p.A = ws.grad[l]; p.Cs = y.cout; p.ntaps = 16;
+      p.plane_stride = (long long)B * y.Hin * y.Win * y.cout;
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          Tap& t = p.taps[kh * 4 + kw];
+          t.plane = (signed char)((((kh + 1) & 1) << 1) | ((kw + 1) & 1));
+          t.dy = (signed char)(kh == 0 ? -1 : (kh == 3 ? 1 : 0));
+          t.dx = (signed char)(kw == 0 ? -1 : (kw == 3 ? 1 : 0));
+        }
+    } else {  // L_FIRST: plain GEMM over (kh,kw,co)
+      p.A = ws.grad[0]; p.Cs = y.k * y.k * y.cout; p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
+    }
+    if (l == 0) {
+      e.kind = EPI_DGRAD_Z;
+      e.out = ws.dz_part;
+      e.nz_out = g->nz_p;
+      p.ksplit = dz_splits_for(B);
+    } else {
+      e.kind = EPI_DGRAD_MASK;
+      e.act = ws.act[l - 1];
+      e.out = ws.grad[l - 1];
+      e.planar_out = g->layers[l - 1].type == L_UP;
+    }
+    DAMC_TRY(run_gemm(g, p, stream));
+  }
+  return DAMC_OK;
+}
+
+int dz_splits(int B) { return dz_splits_for(B); }
+
+}  // namespace damc

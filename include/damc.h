@@ -1,0 +1,125 @@
+/* damc.h -- C ABI of the B200-native sampling library (libdamc_b200.so).
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json:north_star.  The reference has no FFI of its
+ * own: its boundary is the Python call surface of workspace/src/MCMC.py and workspace/src/diffusion_net.py, so every
+ * entry point below cites the reference interface it replaces.  The Python mirror of that surface
+ * (diffusion-amortized-mcmc_b200/damc_b200/MCMC.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless named host_*.
+ *   - all tensors are contiguous fp32 in the reference's own layouts: z [B,nz] row-major, x [B,nc,H,W] (NCHW),
+ *     ConvTranspose2d weight [Cin,Cout,kH,kW], Linear weight [out,in].
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and performs no host
+ *     synchronisation.  Calls are re-entrant for distinct (stream, workspace) pairs.
+ *   - the caller owns every buffer including the workspace; handles own only their packed weights, until damc_free.
+ *   - return value: 0 = ok, non-zero = error; damc_last_error() returns a thread-local message.
+ *   - there is no CPU fallback and no backend dispatch: unsupported configurations are hard errors.
+ */
+#ifndef DAMC_H_
+#define DAMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct damc_handle damc_handle; /* opaque packed-weight handle */
+
+enum { DAMC_OK = 0, DAMC_ERR_INVALID = 1, DAMC_ERR_UNSUPPORTED = 2, DAMC_ERR_CUDA = 3, DAMC_ERR_WORKSPACE = 4 };
+
+/* arithmetic of the generator GEMMs (the EBM, the update and the denoiser are always fp32) */
+enum {
+  DAMC_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM: the rel-1e-3 parity mode                      */
+  DAMC_PREC_BF16 = 1  /* bf16 operands, fp32 accumulate on tcgen05/TMEM fed by TMA: the throughput mode */
+};
+
+int damc_version(void);
+const char* damc_last_error(void);
+int damc_free(damc_handle* h);
+
+/* ---- EBM prior  (replaces netE.ebm : nn.Sequential(Linear,LeakyReLU(.2),Linear,LeakyReLU(.2),Linear),
+ *                  reference src/diffusion_net.py:207-223) ------------------------------------------------------- */
+int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* W3, const float* b3, float negative_slope, void* stream);
+
+/* ---- generator  (replaces netG.gen : ConvTranspose2d / LeakyReLU(.2) / Tanh stack,
+ *                  reference src/diffusion_net.py:20-203) -------------------------------------------------------- */
+typedef struct {
+  int cin, cout, k, stride, pad;
+  const float* weight; /* [cin,cout,k,k] */
+  const float* bias;   /* [cout] or NULL */
+} damc_convt_layer;
+
+int damc_pack_generator(damc_handle** out, int nlayers, const damc_convt_layer* host_layers, float negative_slope,
+                        int precision, void* stream);
+/* output geometry of a packed generator */
+int damc_generator_shape(const damc_handle* gen, int* nz, int* nc, int* height, int* width);
+size_t damc_generator_workspace_bytes(const damc_handle* gen, int B);
+
+/* x_hat = G(z)  (reference: netG.forward, src/diffusion_net.py:49-51; used by gen_samples, src/MCMC.py:126-127) */
+int damc_generator_forward(const damc_handle* gen, const float* z, float* x_hat, int B, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ---- prior Langevin  (replaces sample_langevin_prior_z, reference src/MCMC.py:27-46) --------------------------
+ * z [B,nz] is updated IN PLACE:  z <- z - step^2/2 (dE/dz + z) + step * eps  for K steps in ONE launch.
+ * noise : NULL -> Philox4x32-10 keyed by (seed, chain0 + row, step0 + i); else injected normals [K,B,nz].
+ * trace : NULL, or [K,2] receiving (sum_b E_b, |z|^2/2) evaluated at the pre-update z of every step (:40-41).   */
+int damc_prior_langevin(const damc_handle* ebm, float* z, int B, int K, float step_size, int with_noise,
+                        const float* noise, uint64_t seed, uint64_t chain0, uint64_t step0, float* trace,
+                        void* stream);
+
+/* ---- posterior Langevin  (replaces sample_langevin_post_z_with_prior, reference src/MCMC.py:48-74) -------------
+ * U(z) = |G(z)-x|^2/(2 sigma^2) + E(z) + |z|^2/2 ;  ebm may be NULL (toy-style target without the EBM term).
+ * trace : NULL, or [K,4] receiving (sum E, |G(z)-x|^2/(2 sigma^2), |z|^2/2, mean(grad)) per step (:65-67).
+ * x_hat_out : NULL, or [B,nc,H,W] receiving G(z) of the LAST step's pre-update z.                                */
+int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, float* z, const float* x, int B, int K,
+                            float step_size, float sigma, int with_noise, const float* noise, uint64_t seed,
+                            uint64_t chain0, uint64_t step0, float* trace, float* x_hat_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---- toy posterior  (replaces the closure sample_langevin_post_z, reference toy_example/toy_example.py:110-131;
+ *                      G = ReLU MLP nz-nh-nh-nh-nx, :22-47) ----------------------------------------------------- */
+int damc_pack_toy_mlp(damc_handle** out, int nz, int nh, int nx, const float* const* host_W /*4*/,
+                      const float* const* host_b /*4*/, void* stream);
+int damc_toy_posterior_langevin(const damc_handle* mlp, float* z, const float* x, int B, int K, float step_size,
+                                float sigma, int with_noise, const float* noise, uint64_t seed, uint64_t chain0,
+                                uint64_t step0, void* stream);
+
+/* ---- DAMC denoiser  (replaces the reverse loop of _netQ_U.forward, reference src/diffusion_net.py:595-622, with
+ *                      Q.p = Diffusion_UnetA :463-533 and the helpers src/diffusion_helper_func.py:36-70) ---------- */
+typedef struct {
+  int nz, nxemb, ntemb, nf, residual;
+  const float* time_w1; const float* time_b1; const float* time_w2; const float* time_b2; /* time_mlp.{1,3} */
+  const float* Bproj;                                                                      /* p.B [nz,nz/2]  */
+  /* 7 ConcatSquashLinearSkipCtx layers in execution order: in0,in1,in2,mid0,out0,out1,out2 */
+  int dim_in[7], dim_out[7];
+  const float* W[7];  const float* b[7];   /* _layer.0         [out,in]          */
+  const float* Wc[7]; const float* bc[7];  /* _layer_ctx.1     [out,ntemb+nxemb] */
+  const float* Wg[7]; const float* bg[7];  /* _hyper_gate      [out,out]         */
+  const float* Wb[7];                      /* _hyper_bias      [out,out]         */
+  const float* Ws[7]; const float* bs[7];  /* _skip            [out,in]          */
+} damc_denoiser_desc;
+
+int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* host_desc, void* stream);
+size_t damc_denoise_workspace_bytes(const damc_handle* den, int B, int T);
+
+/* z [B,nz] holds z_T on entry and z_0 on return; xemb [B,nxemb] is encoder(x) or prior_emb(randn).
+ * host_logsnr[T+1]: lambda(t_i) for i = 0..T-1 then unused; computed by the caller exactly as the reference's
+ *   logsnr_schedule_fn (fp32) so the time embedding sees the same argument.
+ * var_type: 0 = 'small', 1 = 'large'.  noise: NULL -> Philox, else [T-1,B,nz] consumed in execution order.
+ * The reference draws eps even when with_noise is false (:616); with injected noise that is immaterial.          */
+int damc_denoise(const damc_handle* den, float* z, const float* xemb, int B, int T, const float* host_logsnr,
+                 int var_type, int with_noise, const float* noise, uint64_t seed, uint64_t chain0, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* single eps-prediction of Q.p (reference src/diffusion_net.py:501-533) -- used by the per-step parity tests */
+int damc_denoiser_eps(const damc_handle* den, const float* z, const float* xemb, float logsnr, float* eps_out, int B,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAMC_H_ */

@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> ctypes -> C ABI -> sm_100a kernels) against the
+reference's golden outputs (tests/golden, produced by the UNMODIFIED reference) and against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): z after K steps with injected noise within rel 1e-3 (fp32 path) and 2e-2 (bf16
+generator path) of the reference.  Ground truth is the reference's fp64 run; because LeakyReLU kink crossings make the
+reference's own fp32 run drift from it, the bound is max(tol, 2 x the reference's fp32 drift).
+"""
+import glob
+import io
+import os
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import damc_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+def relmax(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+
+
+def _names(prefix):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as ge
+    ge.build()
+    return torch.device("cuda:0")
+
+
+def _nets(dataset, nz, ngf, nc, gsd, esd, dev):
+    from damc_b200 import diffusion_net as dn
+    G = dn._netG(dataset, nz, ngf, nc)
+    E = dn._netE(nz)
+    G.load_state_dict(gsd)
+    E.load_state_dict(esd)
+    return G.to(dev), E.to(dev)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", _names("prior_"))
+def test_prior_langevin_golden(name, dev):
+    from damc_b200 import MCMC, diffusion_net as dn
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    nz, B, K = (int(v) for v in g["cfg"])
+    step, noise_on = float(g["step"]), bool(g["noise_on"])
+    E = dn._netE(nz)
+    E.load_state_dict(synth.ebm_state(nz))
+    E = E.to(dev)
+    z0, noise = synth.det_normal("z0", (B, nz)), synth.det_normal("noise", (K, B, nz))
+    z = z0.to(dev).clone().requires_grad_(True)
+    for p in E.parameters():
+        p.requires_grad = False
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = MCMC.sample_langevin_prior_z(z, E, K, step, noise_on, True, noise=noise.to(dev))
+    ref_drift = relmax(g["z_f32"], g["z_f64"])
+    err = relmax(out, g["z_f64"])
+    assert err < max(TOL["fp32"], 2 * ref_drift), (name, err, ref_drift)
+    assert err < 1e-4, (name, err)  # the fp32 MLP loop should in fact be far inside the budget
+    # reference side effects (MCMC.py:36,45-46): in-place update, alias, params trainable again
+    assert out.data_ptr() == z.data_ptr() and not out.requires_grad and z.requires_grad
+    assert all(p.requires_grad for p in E.parameters())
+    # verbose log: same header and step indices as the reference, values agree to print precision
+    ours, theirs = buf.getvalue().strip().split("\n"), str(g["log_f64"]).strip().split("\n")
+    assert ours[0] == theirs[0] == "Log prior sampling."
+    to = [t.split("/") for t in ours[1].replace("Step/en/z_norm: ", "").split()]
+    tt = [t.split("/") for t in theirs[1].replace("Step/en/z_norm: ", "").split()]
+    assert [t[0] for t in to] == [t[0] for t in tt]
+    for a, b in zip(to, tt):
+        assert abs(float(a[1]) - float(b[1])) <= 2e-3 * max(1.0, abs(float(b[1])))
+        assert abs(float(a[2]) - float(b[2])) <= 2e-3 * max(1.0, abs(float(b[2])))
+
+
+@pytest.mark.parametrize("name", _names("post_"))
+def test_posterior_langevin_fp32_golden(name, dev):
+    from damc_b200 import MCMC
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
+    sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
+    layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma)
+    G, E = _nets(str(g["dataset"]), nz, ngf, nc, gsd, esd, dev)
+    z = z0.to(dev).clone().requires_grad_(True)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, step, True,
+                                                     noise=noise.to(dev), precision="fp32")
+    ref_drift = relmax(g["z_f32"], g["z_f64"])
+    err = relmax(out, g["z_f64"])
+    print(f"{name}: ours-vs-fp64 {err:.3e}   reference fp32-vs-fp64 {ref_drift:.3e}")
+    assert err < max(TOL["fp32"], 2 * ref_drift), (name, err, ref_drift)
+    assert out.data_ptr() == z.data_ptr()
+    assert all(p.requires_grad for p in list(G.parameters()) + list(E.parameters()))
+    # G(z_K) crop and the verbose trace agree with the reference
+    xh = MCMC.generator_forward(G, out, precision="fp32")[:, :, :4, :4]
+    assert relmax(xh, g["xhat_f64"]) < max(1e-3, 4 * ref_drift)
+    ours, theirs = buf.getvalue().strip().split("\n"), str(g["log_f64"]).strip().split("\n")
+    assert ours[0] == theirs[0] == "Log posterior sampling."
+    to = [t.split("/") for t in ours[1].replace("Step/cross_entropy/recons_loss: ", "").split()]
+    tt = [t.split("/") for t in theirs[1].replace("Step/cross_entropy/recons_loss: ", "").split()]
+    assert len(to) == len(tt) == K
+    for a, b in zip(to[:3], tt[:3]):  # early steps: before chaotic divergence matters
+        for j in (1, 2, 3):
+            assert abs(float(a[j]) - float(b[j])) <= 5e-3 * max(1.0, abs(float(b[j]))), (a, b)
+
+
+BF16_CASES = ["post_cifar10_full_k5", "post_svhn_full_k5", "post_cifar10_full", "post_svhn_full", "post_mnist_full",
+              "post_celebaHQ_w64"]
+
+
+@pytest.mark.parametrize("name", BF16_CASES)
+def test_posterior_langevin_bf16_golden(name, dev):
+    """bf16 generator path (tensor-core engine): z within rel 2e-2 of the reference (north_star)."""
+    from damc_b200 import MCMC
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
+    sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
+    layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma)
+    G, E = _nets(str(g["dataset"]), nz, ngf, nc, gsd, esd, dev)
+    z = z0.to(dev).clone().requires_grad_(True)
+    out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, step, noise=noise.to(dev),
+                                                 precision="bf16")
+    ref_drift = relmax(g["z_f32"], g["z_f64"])
+    err = relmax(out, g["z_f64"])
+    print(f"{name}: bf16 ours-vs-fp64 {err:.3e}   reference fp32-vs-fp64 {ref_drift:.3e}")
+    assert err < max(TOL["bf16"], 2 * ref_drift), (name, err, ref_drift)
+
+
+@pytest.mark.parametrize("B", [1, 7, 129])
+def test_posterior_ragged_batches_vs_oracle(B, dev):
+    from damc_b200 import MCMC
+    nz, ngf, nc, K, sigma = 100, 16, 3, 3, 0.3
+    layers = synth.gen_layers("svhn", nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=3)
+    G, E = _nets("svhn", nz, ngf, nc, gsd, esd, dev)
+    z = z0.to(dev).clone().requires_grad_(True)
+    out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, True, 0.1, noise=noise.to(dev),
+                                                 precision="fp32")
+    gen = synth.gen_list_from_state(gsd, layers, torch.float64)
+    ebm = synth.ebm_list_from_state(esd, torch.float64)
+    ref = O.langevin_posterior_analytic(z0.double(), x.double(), gen, ebm, K, sigma, True, 0.1, noise.double())
+    assert relmax(out, ref) < 1e-4
+
+
+def test_posterior_without_ebm_and_zero_steps(dev):
+    from damc_b200 import MCMC
+    nz, ngf, nc, B, K, sigma = 8, 16, 1, 5, 4, 1.0
+    layers = synth.gen_layers("mnist", nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=5)
+    G, _ = _nets("mnist", nz, ngf, nc, gsd, esd, dev)
+    z = z0.to(dev).clone().requires_grad_(True)
+    out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, None, K, sigma, False, 0.1, precision="fp32")
+    gen = synth.gen_list_from_state(gsd, layers, torch.float64)
+    ref = O.langevin_posterior_analytic(z0.double(), x.double(), gen, None, K, sigma, False, 0.1)
+    assert relmax(out, ref) < 1e-4
+    z2 = z0.to(dev).clone().requires_grad_(True)
+    out2 = MCMC.sample_langevin_post_z_with_prior(z2, x.to(dev), G, None, 0, sigma, True, 0.1, precision="fp32")
+    assert torch.equal(out2.cpu(), z0)
+
+
+def test_generator_forward_matches_oracle(dev):
+    from damc_b200 import MCMC
+    for dataset, nz, ngf, nc in (("cifar10", 128, 16, 3), ("svhn", 100, 16, 3), ("mnist", 8, 16, 1),
+                                 ("celeba64", 100, 16, 3)):
+        layers = synth.gen_layers(dataset, nz, ngf, nc)
+        gsd = synth.generator_state(layers, seed=2)
+        G, _ = _nets(dataset, nz, ngf, nc, gsd, synth.ebm_state(nz), dev)
+        z = synth.det_normal("zf", (9, nz), 2)
+        ref = O.gen_forward(synth.gen_list_from_state(gsd, layers, torch.float64), z.double())
+        assert relmax(MCMC.generator_forward(G, z.to(dev), precision="fp32"), ref) < 1e-5, dataset
+        with torch.no_grad():  # and the module's own PyTorch forward is the same function
+            assert relmax(G(z.to(dev)), ref) < 1e-3
+
+
+def test_philox_noise_is_shard_invariant_and_normal(dev):
+    """No collective inside sampling: a shard that knows its global chain offset reproduces the single-GPU bits."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    nz, B, K = 128, 96, 7
+    E = dn._netE(nz)
+    E.load_state_dict(synth.ebm_state(nz))
+    E = E.to(dev)
+    z0 = synth.det_normal("z0p", (B, nz)).to(dev)
+    full = MCMC.sample_langevin_prior_z(z0.clone().requires_grad_(True), E, K, 0.4, True, seed=1234)
+    parts = [MCMC.sample_langevin_prior_z(z0[s:s + 32].clone().requires_grad_(True), E, K, 0.4, True, seed=1234,
+                                          chain0=s) for s in (0, 32, 64)]
+    assert torch.equal(full, torch.cat(parts, 0))
+    other = MCMC.sample_langevin_prior_z(z0.clone().requires_grad_(True), E, K, 0.4, True, seed=1235)
+    assert not torch.equal(full, other)
+    # one step with a zero EBM isolates eps:  z' = z (1 - s^2/2) + s eps
+    for p in E.parameters():
+        p.data.zero_()
+    n = 4096
+    zz = torch.zeros(n, nz, device=dev, requires_grad=True)
+    eps = MCMC.sample_langevin_prior_z(zz, E, 1, 1.0, True, seed=7).flatten().double()
+    assert abs(eps.mean().item()) < 5e-3 and abs(eps.var().item() - 1.0) < 1e-2
+    assert abs((eps ** 4).mean().item() - 3.0) < 0.1
+    assert abs(torch.corrcoef(torch.stack([eps[:-1], eps[1:]]))[0, 1].item()) < 5e-3
+
+
+def test_toy_langevin_golden(dev):
+    from damc_b200 import MCMC
+    g = np.load(os.path.join(GOLDEN, "toy.npz"), allow_pickle=True)
+    B, K = (int(v) for v in g["cfg"])
+    dims = [(128, 2), (128, 128), (128, 128), (2, 128)]
+    G = torch.nn.Module()
+    G.net = torch.nn.Sequential(torch.nn.Linear(2, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                                torch.nn.Linear(128, 128), torch.nn.ReLU(), torch.nn.Linear(128, 2))
+    for i, d in enumerate(dims):
+        G.net[2 * i].weight.data.copy_(synth.det_normal(f"toy.w{i}", d, 0, 0.2))
+        G.net[2 * i].bias.data.copy_(synth.det_normal(f"toy.b{i}", (d[0],), 0, 0.1))
+    G = G.to(dev)
+    z0, x, noise = synth.det_normal("toy.z0", (B, 2)), synth.det_normal("toy.x", (B, 2)), \
+        synth.det_normal("toy.noise", (K, B, 2))
+    z = z0.to(dev).clone().requires_grad_(True)
+    out = MCMC.sample_langevin_post_z(z, x.to(dev), G, K, True, float(g["step"]), noise=noise.to(dev))
+    drift = relmax(g["z_f32"], g["z_f64"])
+    assert relmax(out, g["z_f64"]) < max(1e-3, 2 * drift)
+    assert out.data_ptr() == z.data_ptr()
+
+
+@pytest.mark.parametrize("name", _names("damc_"))
+def test_damc_sampler_golden(name, dev):
+    from damc_b200 import MCMC, diffusion_net as dn
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    nz, nxemb, T, B = (int(v) for v in g["cfg"])
+    var_type, with_noise = str(g["var_type"]), bool(g["with_noise"])
+    Q = dn._netQ_U(nc=3, nz=nz, nxemb=nxemb, ntemb=128, nif=64, diffusion_residual=True, n_interval=T,
+                   logsnr_min=-5.1, logsnr_max=9.8, var_type=var_type, with_noise=with_noise, dataset="cifar10")
+    sd = synth.module_state_like(Q, prefix="Q.")
+    Q.load_state_dict(sd)
+    Q = Q.to(dev).eval()
+    zT, noise = synth.det_normal("zT", (B, nz)), synth.det_normal("qnoise", (T - 1, B, nz))
+    xemb = torch.from_numpy(g["xemb"]).to(dev)
+    lam = MCMC.logsnr_table(T, -5.1, 9.8)
+    # (1) per-step eps prediction against the reference: tight
+    for j, i in enumerate((T - 1, T // 2, 1, 0)):
+        eps = MCMC.denoiser_eps(Q, (zT * (0.3 + 0.2 * i / T)).to(dev), float(lam[i]), xemb)
+        assert relmax(eps, g["eps_steps"][j]) < 5e-4, (name, i, relmax(eps, g["eps_steps"][j]))
+    # (2) whole sampler from an image: Q(x) with the reference's draw order (z_T, then T-1 step noises)
+    x = torch.tanh(synth.det_normal("x", (B, 3, 32, 32))).to(dev)
+    z = MCMC.damc_sample(Q, x=x, noise=noise.to(dev), z_init=zT)
+    P64 = synth.denoiser_params_from_state(sd, True, 128, torch.float64)
+    z64 = O.damc_sample(P64, torch.from_numpy(g["xemb"]).double(), zT.double(), T, -5.1, 9.8, var_type, with_noise,
+                        noise.double())
+    ref_err = relmax(g["z_x_f32"], z64)
+    err = relmax(z, z64)
+    print(f"{name}: ours-vs-fp64 {err:.3e}   reference fp32-vs-fp64 {ref_err:.3e}")
+    assert err < max(2.0 * ref_err, 1e-3), (err, ref_err)
