@@ -56,7 +56,7 @@ def test_prior_oracle_matches_reference(name):
         assert relmax(O.ebm_forward(ebm, z), g["en_" + tag]) < max(tol, 1e-6) * 10
         if tag == "f64":
             za = O.langevin_prior_analytic(z0.to(dt), ebm, K, step, noise_on, noise.to(dt))
-            assert relmax(za, g["z_f64"]) < 1e-10
+            assert relmax(za, g["z_f64"]) < 1e-7
             # the logged scalars are the ones the reference prints (MCMC.py:40-41)
             log = str(g["log_f64"])
             for i, en, zn in trace:
