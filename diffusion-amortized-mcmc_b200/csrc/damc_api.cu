@@ -1,5 +1,8 @@
 // damc_api.cu -- extern "C" entry points of libdamc_b200 (declared in include/damc.h).
 #include <stdarg.h>
+#include <atomic>
+#include <utility>
+#include <vector>
 #include <string.h>
 
 #include "damc_common.cuh"
@@ -16,6 +19,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+static size_t g_events_used = 0;
+static bool g_open = false;
+
+void count_launch(int n) { g_launches += n; }
+bool profiling() { return g_profile; }
+void profile_mark(cudaStream_t s, bool begin) {
+  if (!g_profile) return;
+  if (begin) {
+    if (g_events_used == g_events.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      g_events.emplace_back(a, b);
+    }
+    cudaEventRecord(g_events[g_events_used].first, s);
+    g_open = true;
+  } else if (g_open) {
+    cudaEventRecord(g_events[g_events_used].second, s);
+    ++g_events_used;
+    g_open = false;
+  }
+}
+
 int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision, cudaStream_t stream);
 int dz_splits(int B);
 
@@ -27,6 +56,17 @@ static int check_sm100() {
   return DAMC_OK;
 }
 
+int MlpPack::refill(cudaStream_t s) {
+  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+  DAMC_CUDA(cudaMemcpyAsync(W1, src[0], sizeof(float) * ndf * nz, k, s));
+  DAMC_CUDA(cudaMemcpyAsync(b1, src[1], sizeof(float) * ndf, k, s));
+  DAMC_CUDA(cudaMemcpyAsync(W2, src[2], sizeof(float) * ndf * ndf, k, s));
+  DAMC_CUDA(cudaMemcpyAsync(b2, src[3], sizeof(float) * ndf, k, s));
+  DAMC_CUDA(cudaMemcpyAsync(w3, src[4], sizeof(float) * ndf, k, s));
+  DAMC_CUDA(cudaMemcpyAsync(b3, src[5], sizeof(float), k, s));
+  return DAMC_OK;
+}
+
 }  // namespace damc
 
 using namespace damc;
@@ -35,6 +75,32 @@ extern "C" {
 
 int damc_version(void) { return 100; }
 const char* damc_last_error(void) { return g_err; }
+
+long long damc_launch_count(void) { return g_launches.load(); }
+int damc_profile_enable(int on) {
+  g_profile = on != 0;
+  g_events_used = 0;
+  g_open = false;
+  return DAMC_OK;
+}
+int damc_profile_collect(double* gemm_ms, long long* gemm_launches) {
+  double ms = 0.0;
+  for (size_t i = 0; i < g_events_used; ++i) {
+    DAMC_CUDA(cudaEventSynchronize(g_events[i].second));
+    float t = 0.f;
+    DAMC_CUDA(cudaEventElapsedTime(&t, g_events[i].first, g_events[i].second));
+    ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_launches) *gemm_launches = (long long)g_events_used;
+  g_events_used = 0;
+  return DAMC_OK;
+}
+
+int damc_repack(damc_handle* h, void* stream) {
+  if (!h) DAMC_FAIL(DAMC_ERR_INVALID, "damc_repack: null handle");
+  return h->refill((cudaStream_t)stream);
+}
 
 int damc_free(damc_handle* h) {
   delete h;
@@ -58,15 +124,10 @@ int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const flo
   m->b2 = p; p += ndf;
   m->w3 = p; p += ndf;
   m->b3 = p;
-  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
-  cudaMemcpyAsync(m->W1, W1, sizeof(float) * ndf * nz, k, s);
-  cudaMemcpyAsync(m->b1, b1, sizeof(float) * ndf, k, s);
-  cudaMemcpyAsync(m->W2, W2, sizeof(float) * ndf * ndf, k, s);
-  cudaMemcpyAsync(m->b2, b2, sizeof(float) * ndf, k, s);
-  cudaMemcpyAsync(m->w3, W3, sizeof(float) * ndf, k, s);
-  cudaMemcpyAsync(m->b3, b3, sizeof(float), k, s);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { delete m; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_mlp: copy failed: %s", cudaGetErrorString(e)); }
+  const float* srcs[6] = {W1, b1, W2, b2, W3, b3};
+  for (int i = 0; i < 6; ++i) m->src[i] = srcs[i];
+  const int r = m->refill(s);
+  if (r != DAMC_OK) { delete m; return r; }
   *out = m;
   return DAMC_OK;
 }

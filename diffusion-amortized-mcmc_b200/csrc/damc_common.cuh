@@ -30,6 +30,11 @@ void set_error(const char* fmt, ...);
     if (_r != DAMC_OK) return _r; \
   } while (0)
 
+// ---- measurement hooks ------------------------------------------------------------------------------------------
+void count_launch(int n = 1);
+bool profiling();
+void profile_mark(cudaStream_t s, bool begin);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

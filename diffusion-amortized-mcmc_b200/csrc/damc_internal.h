@@ -5,6 +5,8 @@
 struct damc_handle {
   int kind;
   virtual ~damc_handle() {}
+  // re-read the caller's weight tensors recorded at pack time into the packed buffers (async on stream)
+  virtual int refill(cudaStream_t stream) = 0;
 };
 
 namespace damc {
@@ -14,8 +16,10 @@ struct MlpPack : damc_handle {
   int nz = 0, ndf = 0;
   float slope = 0.2f;
   float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  const float* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller's tensors (for damc_repack)
   float* slab = nullptr;
   ~MlpPack() override { if (slab) cudaFree(slab); }
+  int refill(cudaStream_t stream) override;
 };
 
 int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, int with_noise, const float* noise,
@@ -67,7 +71,7 @@ struct GemmPlan {
 struct GenLayer {
   int type, cin, cout, k, stride, pad, Hin, Win, Hout, Wout;
   int cin_p;  // cin padded to a multiple of 64 (first layer: nz)
-  const float* bias = nullptr;           // device copy
+  float* bias = nullptr;                 // device copy
   // packed weights: fwd (per parity class for L_UP: 4, else 1) and dgrad
   void* w_fwd[4] = {nullptr, nullptr, nullptr, nullptr};
   void* w_dgrad = nullptr;
@@ -80,9 +84,11 @@ struct GenPack : damc_handle {
   int nlayers = 0, nz = 0, nz_p = 0, nc = 0, H = 0, W = 0;
   float slope = 0.2f;
   std::vector<GenLayer> layers;
+  std::vector<damc_convt_layer> src;  // caller's tensors (for damc_repack)
   std::vector<void*> allocs;
   int dz_splits = 1;
   ~GenPack() override { for (void* p : allocs) cudaFree(p); }
+  int refill(cudaStream_t stream) override;
 };
 
 struct GenWorkspace {   // carved out of the caller's workspace for a given B

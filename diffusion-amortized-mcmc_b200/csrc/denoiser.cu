@@ -36,7 +36,9 @@ struct DenPack : damc_handle {
   float* Wms[DEN_LAYERS];                     // [din][dout][2]  interleaved (main, skip), transposed
   float* Wgb[DEN_LAYERS];                     // [dout][dout][2] interleaved (gate, hyper-bias), transposed
   float* bias3[DEN_LAYERS];                   // [3][dout]: b_main, b_skip, b_gate
+  damc_denoiser_desc src;                     // caller's tensors (for damc_repack)
   ~DenPack() override { if (slab) cudaFree(slab); }
+  int refill(cudaStream_t stream) override;
 };
 
 // ---- packing ------------------------------------------------------------------------------------------------------
@@ -337,6 +339,29 @@ static DenWs den_ws(const DenPack* d, int B, int T, void* base) {
   return w;
 }
 
+int DenPack::refill(cudaStream_t s) {
+  const damc_denoiser_desc* h = &src;
+  const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+  const int nt = ntemb;
+  DAMC_CUDA(cudaMemcpyAsync(tw1, h->time_w1, sizeof(float) * nt * nt, dd, s));
+  DAMC_CUDA(cudaMemcpyAsync(tb1, h->time_b1, sizeof(float) * nt, dd, s));
+  DAMC_CUDA(cudaMemcpyAsync(tw2, h->time_w2, sizeof(float) * nt * nt, dd, s));
+  DAMC_CUDA(cudaMemcpyAsync(tb2, h->time_b2, sizeof(float) * nt, dd, s));
+  DAMC_CUDA(cudaMemcpyAsync(Bp, h->Bproj, sizeof(float) * nz * (nz / 2), dd, s));
+  for (int i = 0; i < DEN_LAYERS; ++i) {
+    const int di = din[i], dn = dout[i], off = coff[i];
+    pack_interleave_T<<<ceil_div(di * dn, 256), 256, 0, s>>>(h->W[i], h->Ws[i], dn, di, Wms[i]);
+    pack_interleave_T<<<ceil_div(dn * dn, 256), 256, 0, s>>>(h->Wg[i], h->Wb[i], dn, dn, Wgb[i]);
+    pack_ctx_T<<<ceil_div(dn * (nt + nxemb), 256), 256, 0, s>>>(h->Wc[i], dn, nt, nxemb, off, csum, WcT_t, WcT_x);
+    DAMC_CUDA(cudaMemcpyAsync(bias3[i], h->b[i], sizeof(float) * dn, dd, s));
+    DAMC_CUDA(cudaMemcpyAsync(bias3[i] + dn, h->bs[i], sizeof(float) * dn, dd, s));
+    DAMC_CUDA(cudaMemcpyAsync(bias3[i] + 2 * dn, h->bg[i], sizeof(float) * dn, dd, s));
+    DAMC_CUDA(cudaMemcpyAsync(bc + off, h->bc[i], sizeof(float) * dn, dd, s));
+  }
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
 }  // namespace damc
 
 using namespace damc;
@@ -367,16 +392,10 @@ extern "C" int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* h
   if (cudaMalloc(&d->slab, total * sizeof(float)) != cudaSuccess) { delete d; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_denoiser: cudaMalloc failed"); }
   float* p = d->slab;
   auto take = [&](size_t n) { float* r = p; p += n; return r; };
-  const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
   const int nt = h->ntemb;
   d->tw1 = take((size_t)nt * nt); d->tb1 = take(nt); d->tw2 = take((size_t)nt * nt); d->tb2 = take(nt);
   d->Bp = take((size_t)h->nz * (h->nz / 2));
   d->WcT_t = take((size_t)nt * csum); d->WcT_x = take((size_t)h->nxemb * csum); d->bc = take(csum);
-  cudaMemcpyAsync(d->tw1, h->time_w1, sizeof(float) * nt * nt, dd, s);
-  cudaMemcpyAsync(d->tb1, h->time_b1, sizeof(float) * nt, dd, s);
-  cudaMemcpyAsync(d->tw2, h->time_w2, sizeof(float) * nt * nt, dd, s);
-  cudaMemcpyAsync(d->tb2, h->time_b2, sizeof(float) * nt, dd, s);
-  cudaMemcpyAsync(d->Bp, h->Bproj, sizeof(float) * h->nz * (h->nz / 2), dd, s);
   int off = 0;
   for (int i = 0; i < DEN_LAYERS; ++i) {
     const int di = h->dim_in[i], dn = h->dim_out[i];
@@ -384,17 +403,11 @@ extern "C" int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* h
     d->Wms[i] = take(2 * (size_t)di * dn);
     d->Wgb[i] = take(2 * (size_t)dn * dn);
     d->bias3[i] = take(3 * (size_t)dn);
-    pack_interleave_T<<<ceil_div(di * dn, 256), 256, 0, s>>>(h->W[i], h->Ws[i], dn, di, d->Wms[i]);
-    pack_interleave_T<<<ceil_div(dn * dn, 256), 256, 0, s>>>(h->Wg[i], h->Wb[i], dn, dn, d->Wgb[i]);
-    pack_ctx_T<<<ceil_div(dn * (nt + h->nxemb), 256), 256, 0, s>>>(h->Wc[i], dn, nt, h->nxemb, off, csum, d->WcT_t, d->WcT_x);
-    cudaMemcpyAsync(d->bias3[i], h->b[i], sizeof(float) * dn, dd, s);
-    cudaMemcpyAsync(d->bias3[i] + dn, h->bs[i], sizeof(float) * dn, dd, s);
-    cudaMemcpyAsync(d->bias3[i] + 2 * dn, h->bg[i], sizeof(float) * dn, dd, s);
-    cudaMemcpyAsync(d->bc + off, h->bc[i], sizeof(float) * dn, dd, s);
     off += dn;
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { delete d; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_denoiser: %s", cudaGetErrorString(e)); }
+  d->src = *h;
+  const int rr = d->refill(s);
+  if (rr != DAMC_OK) { delete d; return rr; }
   const size_t smem = den_step_smem(d);
   if (smem > 227 * 1024) { delete d; DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "denoiser: step kernel needs %zu B shared memory", smem); }
   *out = d;
@@ -434,6 +447,7 @@ extern "C" int damc_denoise(const damc_handle* den, float* z, const float* xemb,
     den_step_kernel<<<ceil_div(B, DEN_TM), DEN_THREADS, smem, s>>>(a);
   }
   DAMC_CUDA(cudaGetLastError());
+  count_launch(T + 2);
   return DAMC_OK;
 }
 

@@ -359,6 +359,7 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
   const int clusters = ceil_div(B, kChains);
   ebm_langevin_kernel<kChains><<<2 * clusters, 256, P.total, stream>>>(a);
   DAMC_CUDA(cudaGetLastError());
+  count_launch();
   return DAMC_OK;
 }
 

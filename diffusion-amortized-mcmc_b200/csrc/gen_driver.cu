@@ -60,17 +60,22 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
   }
   g->nc = L[nlayers - 1].cout; g->H = H; g->W = W;
 
+  g->src.assign(L, L + nlayers);
+  return g->refill(stream);
+}
+
+// (re)pack every layer's GEMM operands from the caller's ConvTranspose2d tensors; buffers are allocated on first use
+int GenPack::refill(cudaStream_t stream) {
+  GenPack* g = this;
   const size_t es = elem_size(precision);
   for (int i = 0; i < nlayers; ++i) {
     GenLayer& y = g->layers[i];
-    const damc_convt_layer& s = L[i];
+    const damc_convt_layer& s = g->src[i];
     const bool last = i == nlayers - 1;
-    // bias (fp32 device copy; the caller's tensor may be re-used by the optimiser between calls)
-    float* bias = nullptr;
-    DAMC_TRY(dev_alloc(g, (void**)&bias, sizeof(float) * s.cout));
-    if (s.bias) DAMC_CUDA(cudaMemcpyAsync(bias, s.bias, sizeof(float) * s.cout, cudaMemcpyDeviceToDevice, stream));
-    else DAMC_CUDA(cudaMemsetAsync(bias, 0, sizeof(float) * s.cout, stream));
-    y.bias = bias;
+    // bias (fp32 device copy)
+    if (!y.bias) DAMC_TRY(dev_alloc(g, (void**)&y.bias, sizeof(float) * s.cout));
+    if (s.bias) DAMC_CUDA(cudaMemcpyAsync(y.bias, s.bias, sizeof(float) * s.cout, cudaMemcpyDeviceToDevice, stream));
+    else DAMC_CUDA(cudaMemsetAsync(y.bias, 0, sizeof(float) * s.cout, stream));
     // forward operands
     int ntaps, Cs, mode, ncls = 1;
     if (y.type == L_FIRST) { ntaps = 1; Cs = y.cin_p; mode = PK_FIRST_FWD; y.n_fwd = s.k * s.k * s.cout; }
@@ -78,7 +83,7 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
     else { ntaps = 9; Cs = y.cin; mode = PK_SAME_FWD; y.n_fwd = s.cout; }
     y.np_fwd = (int)align_up(y.n_fwd, 16);
     for (int c = 0; c < ncls; ++c) {
-      DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
+      if (!y.w_fwd[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
       DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
                                  precision, y.w_fwd[c], stream));
     }
@@ -88,7 +93,7 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
     else { ntaps = 16; Cs = s.cout; mode = PK_UP_DGRAD; }
     y.n_dg = s.cin;
     y.np_dg = (int)align_up(y.n_dg, 16);
-    DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
+    if (!y.w_dgrad) DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
     DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 0,
                                precision, y.w_dgrad, stream));
   }
@@ -117,7 +122,11 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
 }
 
 static int run_gemm(const GenPack* g, const GemmPlan& p, cudaStream_t stream) {
-  return launch_gemm_simt(p, g->precision, stream);
+  profile_mark(stream, true);
+  const int r = launch_gemm_simt(p, g->precision, stream);
+  profile_mark(stream, false);
+  count_launch();
+  return r;
 }
 
 static void up_fwd_taps(int cls, GemmPlan& p) {
@@ -135,6 +144,7 @@ static void up_fwd_taps(int cls, GemmPlan& p) {
 int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
                       float* xhat, float* loss, cudaStream_t stream) {
   DAMC_TRY(launch_stage_z(z, ws.zin, B, g->nz, g->nz_p, g->precision, stream));
+  count_launch();
   const int L = g->nlayers;
   for (int l = 0; l < L; ++l) {
     const GenLayer& y = g->layers[l];

@@ -14,7 +14,17 @@ namespace damc {
 struct ToyPack : damc_handle {
   int nz = 0, nh = 0, nx = 0;
   float* slab = nullptr;  // W1[nh][nz] b1[nh] W2[nh][nh] b2 W3[nh][nh] b3 W4[nx][nh] b4[nx]
+  const float* src[8] = {};
+  size_t sizes[8] = {};
   ~ToyPack() override { if (slab) cudaFree(slab); }
+  int refill(cudaStream_t stream) override {
+    float* p = slab;
+    for (int i = 0; i < 8; ++i) {
+      DAMC_CUDA(cudaMemcpyAsync(p, src[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+      p += sizes[i];
+    }
+    return DAMC_OK;
+  }
 };
 
 constexpr int TOY_NH = 128, TOY_MAXD = 8, TOY_WARPS = 8, TOY_CPW = 2, TOY_R = TOY_NH / 32;
@@ -244,15 +254,12 @@ extern "C" int damc_pack_toy_mlp(damc_handle** out, int nz, int nh, int nx, cons
   size_t total = 0;
   for (size_t s : sizes) total += s;
   if (cudaMalloc(&t->slab, total * sizeof(float)) != cudaSuccess) { delete t; DAMC_FAIL(DAMC_ERR_CUDA, "cudaMalloc failed"); }
-  float* p = t->slab;
   for (int i = 0; i < 4; ++i) {
-    cudaMemcpyAsync(p, host_W[i], sizes[2 * i] * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-    p += sizes[2 * i];
-    cudaMemcpyAsync(p, host_b[i], sizes[2 * i + 1] * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-    p += sizes[2 * i + 1];
+    t->src[2 * i] = host_W[i]; t->src[2 * i + 1] = host_b[i];
+    t->sizes[2 * i] = sizes[2 * i]; t->sizes[2 * i + 1] = sizes[2 * i + 1];
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { delete t; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_toy_mlp: %s", cudaGetErrorString(e)); }
+  const int r = t->refill((cudaStream_t)stream);
+  if (r != DAMC_OK) { delete t; return r; }
   *out = t;
   return DAMC_OK;
 }
@@ -275,5 +282,6 @@ extern "C" int damc_toy_posterior_langevin(const damc_handle* mlp, float* z, con
   const int per_cta = TOY_WARPS * TOY_CPW;
   toy_langevin_kernel<<<ceil_div(B, per_cta), TOY_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
   DAMC_CUDA(cudaGetLastError());
+  count_launch();
   return DAMC_OK;
 }

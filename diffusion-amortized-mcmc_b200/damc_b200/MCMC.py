@@ -55,11 +55,13 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _f32_cuda(t, what):
+def _f32_cuda(t, what, strict=False):
     if not t.is_cuda:
         raise RuntimeError(f"{what} must be a CUDA tensor (damc_b200 has no CPU fallback); got device {t.device}")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{what} must be float32, got {t.dtype}")
+    if strict and not t.is_contiguous():  # packed handles keep the pointer and re-read it on every call
+        raise RuntimeError(f"{what} must be contiguous")
     return t.detach().contiguous()
 
 
@@ -69,17 +71,22 @@ def _no_hooks(m, what):
 
 
 def _key(params):
-    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+    return tuple((p.data_ptr(), tuple(p.shape), p.dtype, p.is_contiguous()) for p in params)
 
 
 _cache = weakref.WeakKeyDictionary()  # module -> {tag: (key, handle, keepalive)}
 
 
 def _cached(module, tag, params, build):
+    """Packed-weight handle of a module.  Allocations are cached on the identity (storage pointers, shapes) of the
+    parameters; their VALUES are re-read on every call (damc_repack: a few async copy/transpose kernels), because
+    ``param.data.copy_()`` style updates -- e.g. the reference's EMA of Q_dummy, train_gen_recon.py:258-261 -- do not
+    bump tensor version counters and would otherwise leave stale packed weights."""
     slot = _cache.setdefault(module, {})
     key = _key(params)
     hit = slot.get(tag)
     if hit is not None and hit[0] == key:
+        check(lib().damc_repack(hit[1].ptr, _stream(params[0].device)), "damc_repack")
         return hit[1]
     handle, keep = build()
     slot[tag] = (key, handle, keep)
@@ -110,7 +117,7 @@ def pack_ebm(netE):
     params = [p for l in lins for p in (l.weight, l.bias)]
 
     def build():
-        ts = [_f32_cuda(p, "netE parameter") for p in params]
+        ts = [_f32_cuda(p, "netE parameter", True) for p in params]
         out = C.c_void_p()
         check(lib().damc_pack_mlp(C.byref(out), lins[0].in_features, lins[0].out_features,
                                   *[C.c_void_p(t.data_ptr()) for t in ts], s1, _stream(ts[0].device)), "damc_pack_mlp")
@@ -146,8 +153,8 @@ def pack_generator(netG, precision=None):
     def build():
         keep, arr = [], (_lib.ConvTLayer * len(convs))()
         for i, c in enumerate(convs):
-            w = _f32_cuda(c.weight, "netG weight")
-            b = _f32_cuda(c.bias, "netG bias") if c.bias is not None else None
+            w = _f32_cuda(c.weight, "netG weight", True)
+            b = _f32_cuda(c.bias, "netG bias", True) if c.bias is not None else None
             keep += [w, b]
             arr[i] = _lib.ConvTLayer(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0],
                                      w.data_ptr(), b.data_ptr() if b is not None else None)
@@ -331,7 +338,7 @@ def pack_denoiser(Q):
         keep = []
 
         def ptr(t):
-            c = _f32_cuda(t, "Q.p parameter")
+            c = _f32_cuda(t, "Q.p parameter", True)
             keep.append(c)
             return c.data_ptr()
 
@@ -420,8 +427,8 @@ def pack_toy_generator(netG):
     params = [p for l in lins for p in (l.weight, l.bias)]
 
     def build():
-        ws = [_f32_cuda(l.weight, "toy weight") for l in lins]
-        bs = [_f32_cuda(l.bias, "toy bias") for l in lins]
+        ws = [_f32_cuda(l.weight, "toy weight", True) for l in lins]
+        bs = [_f32_cuda(l.bias, "toy bias", True) for l in lins]
         Wp = (C.c_void_p * 4)(*[w.data_ptr() for w in ws])
         bp = (C.c_void_p * 4)(*[t.data_ptr() for t in bs])
         out = C.c_void_p()

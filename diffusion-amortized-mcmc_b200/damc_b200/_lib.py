@@ -30,6 +30,7 @@ SIGNATURES = {
     "damc_version": (_I, []),
     "damc_last_error": (C.c_char_p, []),
     "damc_free": (_I, [_P]),
+    "damc_repack": (_I, [_P, _P]),
     "damc_pack_mlp": (_I, [C.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _P, _F, _P]),
     "damc_pack_generator": (_I, [C.POINTER(_P), _I, C.POINTER(ConvTLayer), _F, _I, _P]),
     "damc_generator_shape": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
@@ -43,6 +44,9 @@ SIGNATURES = {
     "damc_denoise_workspace_bytes": (_SZ, [_P, _I, _I]),
     "damc_denoise": (_I, [_P, _P, _P, _I, _I, C.POINTER(_F), _I, _I, _P, _U64, _U64, _P, _SZ, _P]),
     "damc_denoiser_eps": (_I, [_P, _P, _P, _F, _P, _I, _P, _SZ, _P]),
+    "damc_launch_count": (C.c_longlong, []),
+    "damc_profile_enable": (_I, [_I]),
+    "damc_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

@@ -39,6 +39,10 @@ enum {
 int damc_version(void);
 const char* damc_last_error(void);
 int damc_free(damc_handle* h);
+/* Re-read the caller's weight tensors (the device pointers given at pack time, which must still be alive) into the
+ * packed buffers -- asynchronous on `stream`, no allocation.  The Python mirror calls it before every sampler call, so
+ * in-place parameter updates (optimizer steps, EMA copies through .data as in train_gen_recon.py:258-261) are seen. */
+int damc_repack(damc_handle* h, void* stream);
 
 /* ---- EBM prior  (replaces netE.ebm : nn.Sequential(Linear,LeakyReLU(.2),Linear,LeakyReLU(.2),Linear),
  *                  reference src/diffusion_net.py:207-223) ------------------------------------------------------- */
@@ -118,6 +122,14 @@ int damc_denoise(const damc_handle* den, float* z, const float* xemb, int B, int
 /* single eps-prediction of Q.p (reference src/diffusion_net.py:501-533) -- used by the per-step parity tests */
 int damc_denoiser_eps(const damc_handle* den, const float* z, const float* xemb, float logsnr, float* eps_out, int B,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------------------------
+ * damc_launch_count : cumulative number of kernels this library has launched in the calling process.
+ * damc_profile_enable(1) : bracket every generator GEMM launch with a cudaEvent pair on its own stream;
+ * damc_profile_collect : synchronise those events, return their summed duration (ms) and count, and reset.        */
+long long damc_launch_count(void);
+int damc_profile_enable(int on);
+int damc_profile_collect(double* gemm_ms, long long* gemm_launches);
 
 #ifdef __cplusplus
 }

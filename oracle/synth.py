@@ -15,11 +15,27 @@ def det_normal(name, shape, seed=0, scale=1.0):
     return torch.from_numpy((rs.standard_normal(tuple(shape)) * scale).astype(np.float32))
 
 
+def det_uniform(name, shape, seed=0, bound=1.0):
+    rs = np.random.RandomState((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+    return torch.from_numpy(rs.uniform(-bound, bound, tuple(shape)).astype(np.float32))
+
+
 def generator_state(layers, seed=0, gain=0.85, bias_scale=0.05):
     """layers: list of (cin, cout, k, stride, pad).  Returns state dict with the reference's key names
-    ``gen.{2i}.weight`` [Cin,Cout,k,k] / ``gen.{2i}.bias``.  Scale ~ gain/sqrt(effective fan-in) so that pre-activations
-    stay O(1): LeakyReLU kinks and tanh curvature are exercised, unlike default init."""
+    ``gen.{2i}.weight`` [Cin,Cout,k,k] / ``gen.{2i}.bias``.
+
+    gain > 0 ("trained-like"): N(0, (gain/sqrt(effective fan-in))^2) so that pre-activations stay O(1) and LeakyReLU
+      kinks / tanh curvature are exercised.  At full width this makes the reference's default step
+      (s=0.1, sigma=0.1) expand perturbations ~50x per step, so K-step parity there is only meaningful for small K.
+    gain == 0 ("default-init profile"): U(-b, b) with b = 1/sqrt(Cout k^2), the scale torch's default ConvTranspose2d
+      init produces and the benchmark uses; well conditioned through K = 30."""
     sd = {}
+    if gain == 0:
+        for i, (cin, cout, k, s, p) in enumerate(layers):
+            b = 1.0 / np.sqrt(cout * k * k)
+            sd[f"gen.{2 * i}.weight"] = det_uniform(f"gen.{2 * i}.weight", (cin, cout, k, k), seed, b)
+            sd[f"gen.{2 * i}.bias"] = det_uniform(f"gen.{2 * i}.bias", (cout,), seed, b)
+        return sd
     for i, (cin, cout, k, s, p) in enumerate(layers):
         fan = cin * (k / s) ** 2 if i > 0 else cin
         sd[f"gen.{2 * i}.weight"] = det_normal(f"gen.{2 * i}.weight", (cin, cout, k, k), seed, gain / np.sqrt(fan))

@@ -18,6 +18,9 @@ from oracle import damc_oracle as O
 from oracle import synth
 
 pytestmark = pytest.mark.gpu
+# the goldens were produced on the CPU in true fp32: keep torch's own GPU ops (image encoder) out of TF32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {"fp32": 1e-3, "bf16": 2e-2}
 
@@ -91,7 +94,7 @@ def test_posterior_langevin_fp32_golden(name, dev):
     nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
     sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
     layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
-    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, gain=float(g["gain"]))
     G, E = _nets(str(g["dataset"]), nz, ngf, nc, gsd, esd, dev)
     z = z0.to(dev).clone().requires_grad_(True)
     buf = io.StringIO()
@@ -129,7 +132,7 @@ def test_posterior_langevin_bf16_golden(name, dev):
     nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
     sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
     layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
-    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, gain=float(g["gain"]))
     G, E = _nets(str(g["dataset"]), nz, ngf, nc, gsd, esd, dev)
     z = z0.to(dev).clone().requires_grad_(True)
     out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, step, noise=noise.to(dev),
@@ -138,6 +141,29 @@ def test_posterior_langevin_bf16_golden(name, dev):
     err = relmax(out, g["z_f64"])
     print(f"{name}: bf16 ours-vs-fp64 {err:.3e}   reference fp32-vs-fp64 {ref_drift:.3e}")
     assert err < max(TOL["bf16"], 2 * ref_drift), (name, err, ref_drift)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dataset,nz,ngf,nc", [("cifar10", 128, 128, 3), ("svhn", 100, 64, 3), ("mnist", 8, 128, 1)])
+def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, tol, dev):
+    """One noise-free step at full width with O(1) pre-activations (gain 0.85): dU/dz recovered from the update must
+    match the oracle's analytic gradient.  This isolates kernel arithmetic from the chaotic K-step dynamics that these
+    weights produce at sigma = 0.1 (see oracle/synth.py).  fp32 bound allows an isolated LeakyReLU kink flip."""
+    from damc_b200 import MCMC
+    B, sigma, s = 5, 0.1, 0.1
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, _ = synth.synth_problem(layers, nz, B, 1, sigma, seed=11, gain=0.85)
+    G, E = _nets(dataset, nz, ngf, nc, gsd, esd, dev)
+    gen = synth.gen_list_from_state(gsd, layers, torch.float64)
+    ebm = synth.ebm_list_from_state(esd, torch.float64)
+    _, gG = O.gen_grad(gen, z0.double(), x.double(), sigma)
+    grad_ref = gG + O.ebm_grad(ebm, z0.double())[1] + z0.double()
+    z = z0.to(dev).clone().requires_grad_(True)
+    out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, 1, sigma, False, s, precision=prec)
+    grad = (z0.double() - out.cpu().double()) / (0.5 * s * s)
+    err = relmax(grad, grad_ref)
+    print(f"{dataset} {prec}: dU/dz rel err {err:.3e} (|grad|max {float(grad_ref.abs().max()):.1f})")
+    assert err < tol, (dataset, prec, err)
 
 
 @pytest.mark.parametrize("B", [1, 7, 129])

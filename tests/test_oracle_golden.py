@@ -29,7 +29,7 @@ def test_posterior_oracle_matches_reference(name):
     nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
     sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
     layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
-    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, gain=float(g["gain"]))
     for tag, dt, tol in (("f64", torch.float64, 1e-9), ("f32", torch.float32, 2e-3)):
         gen, ebm = synth.gen_list_from_state(gsd, layers, dt), synth.ebm_list_from_state(esd, dt)
         z = O.langevin_posterior(z0.to(dt), x.to(dt), gen, ebm, K, sigma, noise_on, step, noise.to(dt))
