@@ -1,0 +1,267 @@
+"""Benchmark of the hot path: posterior Langevin chain-steps/sec at CIFAR-10 shape (BASELINE.json:metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference algorithm's CPU port on the host cores)
+
+A "step" is one call of sample_langevin_post_z_with_prior over this rank's batch: B chains x 30 Langevin steps
+(reference defaults: K=30, s=0.1, sigma=0.1, noise on; train_gen_recon.py:383-386) on a CIFAR-10-shaped generator
+(nz=128, ngf=128, 3x32x32) with default-init weights (seed 1) and synthetic images x = clamp(G(z*) + sigma n, -1, 1).
+Chains are independent, so ranks shard them with no collective inside sampling ("scaling": "weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "diffusion-amortized-mcmc_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+NZ, NGF, NC, IMG = 128, 128, 3, 32
+L_STEPS, STEP_SIZE, SIGMA = 30, 0.1, 0.1
+# algorithmic work per chain-step: generator MACs 8.39M + 536.9M + 536.9M + 7.08M, forward + dgrad
+GEN_MACS = 128 * 1024 * 64 + 1024 * 512 * 16 * 64 + 512 * 256 * 16 * 256 + 256 * 3 * 9 * 1024
+FLOP_PER_CHAIN_STEP = 2 * 2 * GEN_MACS
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured (sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_nets(device):
+    import torch
+    from damc_b200 import diffusion_net as dn
+    torch.manual_seed(1)  # reference default seed (train_gen_recon.py:353); default nn init = synthetic weights
+    G, E = dn._netG_cifar10(NZ, NGF, NC), dn._netE(NZ)
+    return G.to(device).eval(), E.to(device).eval()
+
+
+def make_inputs(G, B, device, seed):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    zstar = torch.randn(B, NZ, generator=g)
+    xn = torch.randn(B, NC, IMG, IMG, generator=g)
+    z0 = torch.randn(B, NZ, generator=g)
+    with torch.no_grad():
+        xs = []
+        for i in range(0, B, 512):
+            xs.append(torch.clamp(G(zstar[i:i + 512].to(device)) + SIGMA * xn[i:i + 512].to(device), -1.0, 1.0))
+        x = torch.cat(xs, 0)
+    return z0, x
+
+
+def cpu_reference(B, K, warm=True):
+    """The reference algorithm on the host cores: oracle port of MCMC.py:48-74 (same ATen ops, all threads)."""
+    import torch
+    from oracle import damc_oracle as O
+    from damc_b200 import diffusion_net as dn
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(1)
+    G, E = dn._netG_cifar10(NZ, NGF, NC), dn._netE(NZ)
+    gen = [(G.gen[2 * i].weight.detach(), G.gen[2 * i].bias.detach(), G.gen[2 * i].stride[0], G.gen[2 * i].padding[0])
+           for i in range(4)]
+    ebm = [(E.ebm[2 * i].weight.detach(), E.ebm[2 * i].bias.detach()) for i in range(3)]
+    z0, x = make_inputs(G, B, torch.device("cpu"), 123)
+    if warm:
+        O.langevin_posterior(z0[:8], x[:8], gen, ebm, 1, SIGMA, True, STEP_SIZE)
+    t0 = time.perf_counter()
+    O.langevin_posterior(z0, x, gen, ebm, K, SIGMA, True, STEP_SIZE)
+    dt = time.perf_counter() - t0
+    return B * K / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, K = args.cpu_chains, args.cpu_lsteps
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_reference(B, K, warm=(i == 0))
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "posterior Langevin chain-steps/sec (CIFAR-10 shape)", "value": value,
+            "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cifar10 posterior Langevin, CPU sample of {B} chains x {K} Langevin steps per step",
+                       "nz": NZ, "ngf": NGF, "image": [NC, IMG, IMG], "sigma": SIGMA, "step_size": STEP_SIZE},
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{B} chains x {K} Langevin steps per timed step (oracle/damc_oracle.py)"},
+            "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from damc_b200 import MCMC, _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    B = args.chains
+    G, E = make_nets(dev)
+    z0_host, x = make_inputs(G, B, dev, 1000 + rank)       # different chains on every rank
+    z0_dev = z0_host.to(dev)
+    chain0 = rank * B                                      # global chain index of this shard (Philox key)
+
+    def step(z_init, seed):
+        z = z_init.clone().requires_grad_(True)
+        return MCMC.sample_langevin_post_z_with_prior(z, x, G, E, L_STEPS, SIGMA, True, STEP_SIZE, seed=seed,
+                                                      chain0=chain0, precision=args.precision)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(z0_dev, i)
+    barrier()
+    # ---- timed region: inputs resident in HBM ---------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.damc_profile_enable(1)
+    n0 = lib.damc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        out = step(z0_dev, 100 + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.damc_launch_count() - n0
+    import ctypes
+    gemm_ms, gemm_n = ctypes.c_double(), ctypes.c_longlong()
+    lib.damc_profile_collect(ctypes.byref(gemm_ms), ctypes.byref(gemm_n))
+    lib.damc_profile_enable(0)
+    clk = clocks.stop() if rank == 0 else None
+    assert torch.isfinite(out).all()
+    # ---- end to end: pinned host inputs -> H2D -> public API -> D2H of the chains ------------------------------------
+    xh = x.cpu().pin_memory()
+    zh = z0_host.pin_memory()
+    res = torch.empty(B, NZ).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        xd = xh.to(dev, non_blocking=True)
+        zd = zh.to(dev, non_blocking=True).requires_grad_(True)
+        o = MCMC.sample_langevin_post_z_with_prior(zd, xd, G, E, L_STEPS, SIGMA, True, STEP_SIZE, seed=200 + i,
+                                                   chain0=chain0, precision=args.precision)
+        res.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        pk = peaks()
+        total_cs = world * B * L_STEPS * args.steps
+        value = total_cs / (ms * 1e-3)
+        gemm_flops = B * L_STEPS * args.steps * FLOP_PER_CHAIN_STEP  # this rank's GEMM launches
+        achieved = gemm_flops / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else None
+        cpu_v, cpu_dt = (cpu_reference(args.cpu_chains, args.cpu_lsteps) if world == 1 and not args.no_cpu else (None, None))
+        line = {
+            "metric": "posterior Langevin chain-steps/sec (CIFAR-10 shape)", "value": value, "unit": "chain-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"cifar10 (configs[2]): {B} chains/GPU x {L_STEPS} Langevin steps per step",
+                       "nz": NZ, "ngf": NGF, "image": [NC, IMG, IMG], "sigma": SIGMA, "step_size": STEP_SIZE,
+                       "noise": "philox", "parallelism": f"chains sharded x{world}, no collective in sampling",
+                       "l2": "working set (activations+gradients, %.1f GB/GPU) exceeds the 126 MB L2; no flush needed"
+                             % (B * 461824 * 2 * (2 if args.precision == "bf16" else 4) / 1e9)},
+            "clocks": clk,
+            "e2e": {"value": world * B * L_STEPS * args.steps / (e2e_ms * 1e-3), "unit": "chain-steps/s",
+                    "h2d_bytes_per_step": B * (NC * IMG * IMG + NZ) * 4, "d2h_bytes_per_step": B * NZ * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": None,
+                         "peak_source": pk["src"],
+                         "kernel": "generator implicit-GEMM launches (%d per timed region, %.1f%% of step time)"
+                                   % (gemm_n.value, 100.0 * gemm_ms.value / ms)},
+            "cpu_baseline": None if cpu_v is None else {
+                "value": cpu_v, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{args.cpu_chains} chains x {args.cpu_lsteps} Langevin steps, {cpu_dt:.1f} s "
+                          "(oracle/damc_oracle.py langevin_posterior, torch CPU, all threads)"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DAMC_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--chains", type=int, default=int(os.environ.get("DAMC_BENCH_CHAINS", "1024")),
+                    help="chains per GPU")
+    ap.add_argument("--cpu-chains", type=int, default=128)
+    ap.add_argument("--cpu-lsteps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,12 +143,14 @@ def test_posterior_langevin_bf16_golden(name, dev):
     assert err < max(TOL["bf16"], 2 * ref_drift), (name, err, ref_drift)
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("prec,tol_med,tol_max", [("fp32", 2e-5, 5e-3), ("bf16", 2e-2, 5e-2)])
 @pytest.mark.parametrize("dataset,nz,ngf,nc", [("cifar10", 128, 128, 3), ("svhn", 100, 64, 3), ("mnist", 8, 128, 1)])
-def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, tol, dev):
+def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, tol_med, tol_max, dev):
     """One noise-free step at full width with O(1) pre-activations (gain 0.85): dU/dz recovered from the update must
     match the oracle's analytic gradient.  This isolates kernel arithmetic from the chaotic K-step dynamics that these
-    weights produce at sigma = 0.1 (see oracle/synth.py).  fp32 bound allows an isolated LeakyReLU kink flip."""
+    weights produce at sigma = 0.1 (see oracle/synth.py).  Per-chain errors: the median chain must be at rounding level;
+    the worst chain may carry an isolated LeakyReLU kink flip (a pre-activation within rounding of 0 takes slope 1 in
+    one implementation and 0.2 in the other), which moves that chain's gradient by ~1e-3 of its magnitude."""
     from damc_b200 import MCMC
     B, sigma, s = 5, 0.1, 0.1
     layers = synth.gen_layers(dataset, nz, ngf, nc)
@@ -161,9 +163,10 @@ def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, t
     z = z0.to(dev).clone().requires_grad_(True)
     out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, 1, sigma, False, s, precision=prec)
     grad = (z0.double() - out.cpu().double()) / (0.5 * s * s)
-    err = relmax(grad, grad_ref)
-    print(f"{dataset} {prec}: dU/dz rel err {err:.3e} (|grad|max {float(grad_ref.abs().max()):.1f})")
-    assert err < tol, (dataset, prec, err)
+    per_chain = ((grad - grad_ref).abs().amax(1) / grad_ref.abs().amax(1)).numpy()
+    print(f"{dataset} {prec}: dU/dz per-chain rel err median {np.median(per_chain):.3e} max {per_chain.max():.3e} "
+          f"(|grad|max {float(grad_ref.abs().max()):.1f})")
+    assert np.median(per_chain) < tol_med and per_chain.max() < tol_max, (dataset, prec, per_chain)
 
 
 @pytest.mark.parametrize("B", [1, 7, 129])
