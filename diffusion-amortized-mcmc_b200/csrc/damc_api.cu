@@ -46,7 +46,7 @@ void profile_mark(cudaStream_t s, bool begin) {
 }
 
 int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision, cudaStream_t stream);
-int dz_splits(int B);
+int dz_splits(const GenPack* g, int B);
 
 static int check_sm100() {
   int dev = 0, major = 0;
@@ -203,7 +203,7 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
   // unused im2col slots (image border taps, channel padding) must read as zero; live slots are rewritten every step
   DAMC_CUDA(cudaMemsetAsync(ws.gcol, 0, elem_size(g->precision) * (size_t)B * last.Hin * last.Win * 64, s));
   if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 4 * K, s));
-  const int S = dz_splits(B);
+  const int S = dz_splits(g, B);
   for (int i = 0; i < K; ++i) {
     float* tr = trace ? trace + 4 * (size_t)i : nullptr;
     DAMC_TRY(generator_forward(g, ws, z, B, x, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, s));

@@ -62,7 +62,8 @@ struct GemmPlan {
   int B, Hm, Wm, Cs;        // M grid and K per tap (multiple of 64)
   int ntaps;
   Tap taps[16];
-  const void* W;            // SIMT: [ntaps*Cs][Np] fp32/bf16 (N contiguous);  TC: [ntaps][Np][Cs] bf16 (K contiguous)
+  const void* W;            // SIMT engine: [ntaps*Cs][Np] fp32/bf16 (N contiguous)
+  const void* Wtc;          // tcgen05 engine: [ntaps][Np][Cs] bf16 (K contiguous), or null
   int N, Np;                // logical / padded (multiple of 16) output columns
   int ksplit;               // >1: grid.z splits the K loop (EPI_DGRAD_Z only)
   Epilogue epi;
@@ -75,6 +76,8 @@ struct GenLayer {
   // packed weights: fwd (per parity class for L_UP: 4, else 1) and dgrad
   void* w_fwd[4] = {nullptr, nullptr, nullptr, nullptr};
   void* w_dgrad = nullptr;
+  void* w_fwd_tc[4] = {nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tcgen05 engine (bf16 mode)
+  void* w_dgrad_tc = nullptr;
   int n_fwd = 0, np_fwd = 0;    // N / padded N of the forward GEMM
   int n_dg = 0, np_dg = 0;      // N / padded N of the dgrad GEMM
 };
@@ -87,6 +90,7 @@ struct GenPack : damc_handle {
   std::vector<damc_convt_layer> src;  // caller's tensors (for damc_repack)
   std::vector<void*> allocs;
   int dz_splits = 1;
+  bool use_tc = false;      // bf16 mode: tcgen05 engine (default) or the SIMT engine on bf16 storage (DAMC_TC=0)
   ~GenPack() override { for (void* p : allocs) cudaFree(p); }
   int refill(cudaStream_t stream) override;
 };

@@ -3,6 +3,8 @@
 //
 // Replaces, per Langevin step, netG(z) + autograd.grad through netG of sample_langevin_post_z_with_prior (reference
 // workspace/src/MCMC.py:55-60) for the generator families of workspace/src/diffusion_net.py:20-203.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "damc_common.cuh"
@@ -10,9 +12,14 @@
 
 namespace damc {
 
-static int dz_splits_for(int B) {
+// split-K factor of the first layer's dgrad (M = chains only): enough tiles to fill the SMs, no empty K range
+static int dz_splits_for(const GenPack* g, int B) {
   const int mt = ceil_div(B, 128);
-  return std::max(1, std::min(32, 296 / mt));
+  const GenLayer& f = g->layers[0];
+  const int kb = f.k * f.k * f.cout / 64;
+  int s = std::max(1, std::min(std::min(32, kb), 296 / mt));
+  while (s > 1 && (long long)ceil_div(kb, s) * (s - 1) >= kb) --s;
+  return s;
 }
 
 static int dev_alloc(GenPack* g, void** p, size_t bytes) {
@@ -61,6 +68,9 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
   g->nc = L[nlayers - 1].cout; g->H = H; g->W = W;
 
   g->src.assign(L, L + nlayers);
+  const char* env = getenv("DAMC_TC");
+  g->use_tc = precision == DAMC_PREC_BF16 && !(env && env[0] == '0');
+  if (g->use_tc && !tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "bf16 mode needs cuTensorMapEncodeTiled from the driver (no fallback)");
   return g->refill(stream);
 }
 
@@ -86,6 +96,11 @@ int GenPack::refill(cudaStream_t stream) {
       if (!y.w_fwd[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
       DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
                                  precision, y.w_fwd[c], stream));
+      if (use_tc) {
+        if (!y.w_fwd_tc[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd_tc[c], es * (size_t)ntaps * Cs * y.np_fwd));
+        DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 1,
+                                   precision, y.w_fwd_tc[c], stream));
+      }
     }
     // dgrad operands
     if (last) { ntaps = 1; Cs = 64; mode = PK_LAST_DGRAD_COL; }
@@ -96,6 +111,11 @@ int GenPack::refill(cudaStream_t stream) {
     if (!y.w_dgrad) DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
     DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 0,
                                precision, y.w_dgrad, stream));
+    if (use_tc) {
+      if (!y.w_dgrad_tc) DAMC_TRY(dev_alloc(g, &y.w_dgrad_tc, es * (size_t)ntaps * Cs * y.np_dg));
+      DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 1,
+                                 precision, y.w_dgrad_tc, stream));
+    }
   }
   return DAMC_OK;
 }
@@ -116,14 +136,14 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   }
   const GenLayer& last = g->layers[L - 1];
   ws->gcol = take(es * (size_t)B * last.Hin * last.Win * 64);
-  ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(B) * B * g->nz_p);
+  ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(g, B) * B * g->nz_p);
   ws->bytes = o;
   return DAMC_OK;
 }
 
 static int run_gemm(const GenPack* g, const GemmPlan& p, cudaStream_t stream) {
   profile_mark(stream, true);
-  const int r = launch_gemm_simt(p, g->precision, stream);
+  const int r = (g->use_tc && p.Wtc) ? launch_gemm_tc(p, stream) : launch_gemm_simt(p, g->precision, stream);
   profile_mark(stream, false);
   count_launch();
   return r;
@@ -173,12 +193,12 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     }
     if (y.type == L_FIRST) {
       p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
-      p.W = y.w_fwd[0];
+      p.W = y.w_fwd[0]; p.Wtc = y.w_fwd_tc[0];
       DAMC_TRY(run_gemm(g, p, stream));
     } else if (y.type == L_UP) {
       for (int cls = 0; cls < 4; ++cls) {
         up_fwd_taps(cls, p);
-        p.W = y.w_fwd[cls];
+        p.W = y.w_fwd[cls]; p.Wtc = y.w_fwd_tc[cls];
         e.py = cls >> 1; e.px = cls & 1;
         DAMC_TRY(run_gemm(g, p, stream));
       }
@@ -186,7 +206,7 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
       p.ntaps = 9;
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = Tap{0, (signed char)(1 - kh), (signed char)(1 - kw), 0};
-      p.W = y.w_fwd[0];
+      p.W = y.w_fwd[0]; p.Wtc = y.w_fwd_tc[0];
       DAMC_TRY(run_gemm(g, p, stream));
     }
   }
@@ -200,7 +220,7 @@ int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_
     GemmPlan p{};
     p.B = B; p.Hm = y.Hin; p.Wm = y.Win;
     p.N = y.n_dg; p.Np = y.np_dg; p.ksplit = 1;
-    p.W = y.w_dgrad;
+    p.W = y.w_dgrad; p.Wtc = y.w_dgrad_tc;
     Epilogue& e = p.epi;
     e.slope = g->slope;
     if (l == L - 1) {  // im2col'd dL/dh written by the forward epilogue
@@ -222,7 +242,7 @@ int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_
       e.kind = EPI_DGRAD_Z;
       e.out = ws.dz_part;
       e.nz_out = g->nz_p;
-      p.ksplit = dz_splits_for(B);
+      p.ksplit = dz_splits_for(g, B);
     } else {
       e.kind = EPI_DGRAD_MASK;
       e.act = ws.act[l - 1];
@@ -234,6 +254,6 @@ int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_
   return DAMC_OK;
 }
 
-int dz_splits(int B) { return dz_splits_for(B); }
+int dz_splits(const GenPack* g, int B) { return dz_splits_for(g, B); }
 
 }  // namespace damc

@@ -1,0 +1,461 @@
+// gen_tc.cu -- tcgen05 / TMEM / TMA engine for the generator's shifted-window GEMMs (DAMC_PREC_BF16).
+//
+// Replaces the cuDNN conv-transpose forward and dgrad kernels PyTorch dispatches for netG(z) and autograd.grad through
+// netG (reference workspace/src/MCMC.py:55-60, diffusion_net.py:26-45).  Same formulation as gen_simt.cu -- every layer
+// pass is  D[m,n] = sum_taps A_tap[m,:] . W_tap[n,:]  with A_tap a shifted window of an NHWC (or parity-planar) tensor --
+// but the operands are bf16, fetched by TMA and multiplied by the 5th-generation tensor cores into TMEM:
+//
+//   * A tile  : one TMA 5-D box {64 ch, W, Ht, Bt, plane} of the source tensor at a tap-shifted coordinate.  Rows of
+//               the box are pixels, each 64 bf16 = one 128-byte swizzle row, so the box lands directly in the UMMA
+//               K-major SWIZZLE_128B layout; out-of-image taps are zero-filled by the TMA unit (no padding, no im2col).
+//   * B tile  : TMA 2-D box {64, BN} of the pre-packed weights [tap][n][c] (K-major as well).
+//   * MMA     : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN <= 256, K = 16 x 4 per 64-channel block, fp32
+//               accumulators in TMEM (2 x 256 columns: the epilogue of tile i overlaps the main loop of tile i+1).
+//   * roles   : warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..5 = epilogue (tcgen05.ld, fused
+//               bias / LeakyReLU / mask / tanh-likelihood, 16-byte stores).  Persistent CTAs, one per SM, static tile
+//               order with the N tiles of one M tile adjacent (A re-reads hit L2).
+#include <cuda.h>
+
+#include "damc_common.cuh"
+#include "damc_internal.h"
+#include "gen_epilogue.cuh"
+
+namespace damc {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+
+struct TcParams {
+  GemmPlan plan;
+  int BN, stages, b_stage_bytes;
+  int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
+  int Ht, Bt, tiles_per_img, tile_rows;
+  uint32_t a_box_bytes, b_box_bytes, idesc;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must trap (error reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 27)) __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]   (both operands K-major, bf16, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major SWIZZLE_128B: 8-row groups of 128-byte rows, 1024 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100), bits [46,48)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---- epilogue for one row x 16 consecutive columns ---------------------------------------------------------------------
+struct RowCtx {
+  bool ok;
+  int m, b, y, x;
+};
+
+__device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, int split, int n0, const uint32_t raw[16],
+                                            float& loss_acc) {
+  const Epilogue& e = p.epi;
+  if (!r.ok || n0 >= p.N) return;
+  if (e.kind == EPI_FWD_ACT && n0 + 16 <= p.N) {
+    const long long o = (long long)r.b * e.o_b + (long long)(r.y * e.sy + e.py) * e.o_y +
+                        (long long)(r.x * e.sx + e.px) * e.o_x + n0;
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + (n0 % e.bias_mod));
+    uint32_t w[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = __ldg(bp + q);
+      float h0 = __uint_as_float(raw[4 * q + 0]) + bb.x, h1 = __uint_as_float(raw[4 * q + 1]) + bb.y;
+      float h2 = __uint_as_float(raw[4 * q + 2]) + bb.z, h3 = __uint_as_float(raw[4 * q + 3]) + bb.w;
+      h0 = h0 > 0.f ? h0 : e.slope * h0; h1 = h1 > 0.f ? h1 : e.slope * h1;
+      h2 = h2 > 0.f ? h2 : e.slope * h2; h3 = h3 > 0.f ? h3 : e.slope * h3;
+      w[2 * q] = pack_bf16x2(h0, h1);
+      w[2 * q + 1] = pack_bf16x2(h2, h3);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    return;
+  }
+  if (e.kind == EPI_DGRAD_MASK && n0 + 16 <= p.N) {
+    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.act) + (long long)r.m * p.N + n0);
+    long long o;
+    if (e.planar_out) {
+      const int Hh = p.Hm >> 1, Wh = p.Wm >> 1;
+      o = (long long)((r.y & 1) * 2 + (r.x & 1)) * p.B * Hh * Wh * p.N +
+          (((long long)r.b * Hh + (r.y >> 1)) * Wh + (r.x >> 1)) * p.N + n0;
+    } else {
+      o = (long long)r.m * p.N + n0;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o);
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const uint4 a = __ldg(ap + hlf);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // bf16 sign/zero test on the raw bits: positive and non-zero  <=>  (bits & 0x7fff) != 0 && sign == 0
+        const uint32_t lo = aw[q] & 0xffffu, hi = aw[q] >> 16;
+        const float s0 = (lo != 0u && lo < 0x8000u) ? 1.f : e.slope;
+        const float s1 = (hi != 0u && hi < 0x8000u) ? 1.f : e.slope;
+        w[q] = pack_bf16x2(__uint_as_float(raw[8 * hlf + 2 * q]) * s0, __uint_as_float(raw[8 * hlf + 2 * q + 1]) * s1);
+      }
+      dst[hlf] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j)
+    if (n0 + j < p.N)
+      epilogue_elem<__nv_bfloat16>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment of the tile ring is required by SWIZZLE_128B
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
+  const uint32_t bars = smem_base + (uint32_t)P.stages * stage_bytes;  // [full x S][empty x S][tfull x 2][tempty x 2][tmem ptr]
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (P.stages + s); };
+  auto bar_tfull = [&](int a) { return bars + 8u * (2 * P.stages + a); };
+  auto bar_tempty = [&](int a) { return bars + 8u * (2 * P.stages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * P.stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const GemmPlan& p = P.plan;
+  const int total_tiles = P.m_tiles * P.n_tiles * p.ksplit;
+
+  auto decode = [&](int tile, int& mt, int& nt, int& sp) {
+    nt = tile % P.n_tiles;
+    const int r = tile / P.n_tiles;
+    mt = r % P.m_tiles;
+    sp = r / P.m_tiles;
+  };
+  auto tile_origin = [&](int mt, int& b0, int& y0) {
+    if (P.Bt == 1) { b0 = mt / P.tiles_per_img; y0 = (mt - b0 * P.tiles_per_img) * P.Ht; }
+    else { b0 = mt * P.Bt; y0 = 0; }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt, sp, b0, y0;
+        decode(tile, mt, nt, sp);
+        tile_origin(mt, b0, y0);
+        const int kb0 = sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int t = kb / P.kb_per_tap, c0 = (kb - t * P.kb_per_tap) * TC_BK;
+          const Tap tp = p.taps[t];
+          mbar_wait(bar_empty(stage), phase ^ 1u);
+          mbar_expect_tx(bar_full(stage), P.a_box_bytes + P.b_box_bytes);
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          tma_load_5d(sa, &tmA, bar_full(stage), c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
+          tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, t * p.Np + nt * P.BN);
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int mt, nt, sp;
+        decode(tile, mt, nt, sp);
+        const int kb0 = sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_tempty(as), aphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_empty(stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (kb1 <= kb0) {  // empty K range (trailing split): nothing was accumulated -> signal with zeros impossible;
+          // the host guarantees kb_per_split * (ksplit-1) < kb_total, so this cannot happen
+        }
+        umma_commit(bar_tfull(as));  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    float loss_acc = 0.f;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int mt, nt, sp, b0, y0;
+      decode(tile, mt, nt, sp);
+      tile_origin(mt, b0, y0);
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      // row of this thread inside the tile -> (chain, y, x) on the M grid
+      const int r = q * 32 + lane;
+      RowCtx rc;
+      {
+        const int per_img = P.Ht * p.Wm;
+        const int bt = r / per_img, rem = r - bt * per_img;
+        rc.b = b0 + bt;
+        rc.y = y0 + rem / p.Wm;
+        rc.x = rem % p.Wm;
+        rc.ok = r < P.tile_rows && rc.b < p.B && rc.y < p.Hm;
+        rc.m = (rc.b * p.Hm + rc.y) * p.Wm + rc.x;
+      }
+      mbar_wait(bar_tfull(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+      for (int c = 0; c < P.BN; c += 32) {
+        uint32_t v[32];
+        if (c + 32 <= P.BN) {
+          tmem_ld32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+          epi_chunk16(p, rc, sp, nt * P.BN + c + 16, v + 16, loss_acc);
+        } else {
+          tmem_ld16(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(as));
+    }
+    if (p.epi.kind == EPI_FWD_LAST && p.epi.loss != nullptr) {
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0 && loss_acc != 0.f) atomicAdd(p.epi.loss, loss_acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+int tc_available() { return get_encode() != nullptr; }
+
+int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (p.Cs % TC_BK) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, TC_BK);
+  if (p.Np % 16) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: padded N (%d) must be a multiple of 16", p.Np);
+  if (p.Wm > TC_BM) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: pixel-grid width %d > %d", p.Wm, TC_BM);
+  TcParams P{};
+  P.plan = p;
+  P.BN = p.Np < 256 ? p.Np : 256;
+  P.n_tiles = ceil_div(p.Np, P.BN);
+  if (p.Hm * p.Wm >= TC_BM) {
+    P.Bt = 1;
+    P.Ht = TC_BM / p.Wm;
+    P.tiles_per_img = ceil_div(p.Hm, P.Ht);
+    P.m_tiles = p.B * P.tiles_per_img;
+  } else {
+    P.Ht = p.Hm;
+    P.Bt = TC_BM / (p.Hm * p.Wm);
+    P.tiles_per_img = 1;
+    P.m_tiles = ceil_div(p.B, P.Bt);
+  }
+  P.tile_rows = p.Wm * P.Ht * P.Bt;
+  P.kb_per_tap = p.Cs / TC_BK;
+  P.kb_total = p.ntaps * P.kb_per_tap;
+  P.kb_per_split = ceil_div(P.kb_total, p.ksplit);
+  if ((long long)P.kb_per_split * (p.ksplit - 1) >= P.kb_total)
+    DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: ksplit %d leaves an empty K range (%d blocks)", p.ksplit, P.kb_total);
+  P.a_box_bytes = (uint32_t)P.tile_rows * TC_BK * 2;
+  P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
+  P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
+  const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
+  P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048) / stage_bytes));
+  // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  CUtensorMap tmA, tmB;
+  {
+    const int nplanes = [&] { int mx = 0; for (int t = 0; t < p.ntaps; ++t) mx = std::max(mx, (int)p.taps[t].plane); return mx + 1; }();
+    const cuuint64_t dims[5] = {(cuuint64_t)p.Cs, (cuuint64_t)p.Wm, (cuuint64_t)p.Hm, (cuuint64_t)p.B, (cuuint64_t)nplanes};
+    const cuuint64_t row = (cuuint64_t)p.Cs * 2;
+    const cuuint64_t plane_bytes = nplanes > 1 ? (cuuint64_t)p.plane_stride * 2 : row * p.Wm * p.Hm * p.B;
+    const cuuint64_t strides[4] = {row, row * p.Wm, row * p.Wm * p.Hm, plane_bytes};
+    const cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)p.Wm, (cuuint32_t)P.Ht, (cuuint32_t)P.Bt, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p.A), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (Cs=%d W=%d H=%d B=%d planes=%d)", (int)r, p.Cs, p.Wm, p.Hm, p.B, nplanes);
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)p.ntaps * p.Np};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)P.BN};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d (Cs=%d rows=%d BN=%d)", (int)r, p.Cs, p.ntaps * p.Np, P.BN);
+  }
+  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DAMC_CUDA(cudaGetDevice(&dev));
+    DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = P.m_tiles * P.n_tiles * p.ksplit;
+  convgemm_tc_kernel<<<std::min(total, num_sms), TC_THREADS, smem, stream>>>(tmA, tmB, P);
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+}  // namespace damc
