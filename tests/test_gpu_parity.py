@@ -143,7 +143,7 @@ def test_posterior_langevin_bf16_golden(name, dev):
     assert err < max(TOL["bf16"], 2 * ref_drift), (name, err, ref_drift)
 
 
-@pytest.mark.parametrize("prec,tol_med,tol_max", [("fp32", 2e-5, 5e-3), ("bf16", 2e-2, 5e-2)])
+@pytest.mark.parametrize("prec,tol_med,tol_max", [("fp32", 2e-5, 5e-3), ("bf16", 4e-2, 8e-2)])
 @pytest.mark.parametrize("dataset,nz,ngf,nc", [("cifar10", 128, 128, 3), ("svhn", 100, 64, 3), ("mnist", 8, 128, 1)])
 def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, tol_med, tol_max, dev):
     """One noise-free step at full width with O(1) pre-activations (gain 0.85): dU/dz recovered from the update must
