@@ -11,10 +11,11 @@
 //   * B tile  : TMA 2-D box {64, BN} of the pre-packed weights [tap][n][c] (K-major as well).
 //   * MMA     : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN <= 256, K = 16 x 4 per 64-channel block, fp32
 //               accumulators in TMEM (2 x 256 columns: the epilogue of tile i overlaps the main loop of tile i+1).
-//   * roles   : warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..5 = epilogue (tcgen05.ld, fused
+//   * roles   : warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..9 = epilogue (tcgen05.ld, fused
 //               bias / LeakyReLU / mask / tanh-likelihood, 16-byte stores).  Persistent CTAs, one per SM, static tile
 //               order with the N tiles of one M tile adjacent (A re-reads hit L2).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "damc_common.cuh"
 #include "damc_internal.h"
@@ -22,8 +23,9 @@
 
 namespace damc {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
+constexpr int TC_BM = 128, TC_BK = 64, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 32 * 64 * 2;  // per epilogue warp: 32 rows x 64 bf16
 
 struct TcParams {
   GemmPlan plan;
@@ -31,6 +33,7 @@ struct TcParams {
   int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
   int Ht, Bt, tiles_per_img, tile_rows;
   uint32_t a_box_bytes, b_box_bytes, idesc;
+  int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -207,6 +210,106 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
       epilogue_elem<__nv_bfloat16>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
 }
 
+// ---- staged epilogue: TMEM -> registers -> (bias+LeakyReLU | mask) -> swizzled smem -> coalesced 16-byte row stores ------
+// CPR = 16-byte chunks per row segment (8: 64 columns, 16: 128 columns).  All global accesses are issued in unrolled
+// batches so that a warp keeps 32/CPR x 16 independent 16-byte requests in flight.
+template <int CPR>
+__device__ __forceinline__ void staged_epilogue(const TcParams& P, const RowCtx& rc, int nt, uint32_t t_row,
+                                                uint32_t my_stage, int lane, int grp) {
+  const GemmPlan& p = P.plan;
+  const Epilogue& e = p.epi;
+  constexpr int SW = CPR * 8, RPI = 32 / CPR, NIT = 32 / RPI;
+  constexpr uint32_t row_bytes = SW * 2;
+  const bool is_mask = e.kind == EPI_DGRAD_MASK;
+  const __nv_bfloat16* act_row = nullptr;
+  __nv_bfloat16* out_row = nullptr;
+  if (rc.ok) {
+    if (is_mask) {
+      act_row = reinterpret_cast<const __nv_bfloat16*>(e.act) + (long long)rc.m * p.N;
+      long long o;
+      if (e.planar_out) {
+        const int Hh = p.Hm >> 1, Wh = p.Wm >> 1;
+        o = (long long)((rc.y & 1) * 2 + (rc.x & 1)) * p.B * Hh * Wh * p.N +
+            (((long long)rc.b * Hh + (rc.y >> 1)) * Wh + (rc.x >> 1)) * p.N;
+      } else {
+        o = (long long)rc.m * p.N;
+      }
+      out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
+    } else {
+      out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)rc.b * e.o_b +
+                (long long)(rc.y * e.sy + e.py) * e.o_y + (long long)(rc.x * e.sx + e.px) * e.o_x;
+    }
+  }
+  const unsigned long long act_bits = (unsigned long long)act_row, out_bits = (unsigned long long)out_row;
+  const int sub = lane / CPR, j = lane % CPR;
+  for (int seg = grp * SW; seg < P.BN; seg += 2 * SW) {  // the two warps of a lane quarter alternate segments
+    const int n_base = nt * P.BN + seg;
+    if (n_base >= p.N) break;
+    if (is_mask) {  // coalesced, batched load of the activation rows (sign source) into the staging buffer
+      uint4 a[NIT];
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const unsigned long long pb = __shfl_sync(0xffffffffu, act_bits, i * RPI + sub);
+        a[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (pb) a[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pb) + n_base) + j);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int R = i * RPI + sub;
+        const uint32_t dst = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a[i].x), "r"(a[i].y), "r"(a[i].z), "r"(a[i].w) : "memory");
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < SW; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_row + (uint32_t)(seg + c), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int jj = (c >> 3) + g;
+        const uint32_t addr = my_stage + (uint32_t)lane * row_bytes + (uint32_t)((jj ^ (lane & (CPR - 1))) << 4);
+        uint32_t w[4];
+        if (is_mask) {
+          uint32_t aw[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(aw[0]), "=r"(aw[1]), "=r"(aw[2]), "=r"(aw[3]) : "r"(addr) : "memory");
+#pragma unroll
+          for (int t2 = 0; t2 < 4; ++t2) {
+            const uint32_t lo = aw[t2] & 0xffffu, hi = aw[t2] >> 16;
+            const float s0 = (lo != 0u && lo < 0x8000u) ? 1.f : e.slope;
+            const float s1 = (hi != 0u && hi < 0x8000u) ? 1.f : e.slope;
+            w[t2] = pack_bf16x2(__uint_as_float(v[8 * g + 2 * t2]) * s0, __uint_as_float(v[8 * g + 2 * t2 + 1]) * s1);
+          }
+        } else {
+          const float4* bp = reinterpret_cast<const float4*>(e.bias + ((n_base + c + 8 * g) % e.bias_mod));
+          const float4 b0v = __ldg(bp), b1v = __ldg(bp + 1);
+          const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+          for (int t2 = 0; t2 < 4; ++t2) {
+            float h0 = __uint_as_float(v[8 * g + 2 * t2]) + bb[2 * t2], h1 = __uint_as_float(v[8 * g + 2 * t2 + 1]) + bb[2 * t2 + 1];
+            h0 = h0 > 0.f ? h0 : e.slope * h0;
+            h1 = h1 > 0.f ? h1 : e.slope * h1;
+            w[t2] = pack_bf16x2(h0, h1);
+          }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {  // write-out: CPR consecutive lanes cover one contiguous row segment
+      const int R = i * RPI + sub;
+      const unsigned long long pb = __shfl_sync(0xffffffffu, out_bits, R);
+      const uint32_t src = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
+      uint4 o4;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "r"(src) : "memory");
+      if (pb) *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pb) + n_base) + j) = o4;
+    }
+    __syncwarp();
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -221,6 +324,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto bar_tfull = [&](int a) { return bars + 8u * (2 * P.stages + a); };
   auto bar_tempty = [&](int a) { return bars + 8u * (2 * P.stages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * P.stages + 4);
+  const uint32_t staging = (tmem_slot + 16u + 127u) & ~127u;  // [4 warps][32 rows][<=256 B], XOR-swizzled 16-B chunks
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -229,7 +333,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
@@ -307,8 +411,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;  // two warps share a quarter and split the columns
     int it = 0;
     float loss_acc = 0.f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -332,7 +437,10 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(bar_tfull(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
-      for (int c = 0; c < P.BN; c += 32) {
+      if (P.stage_cols == 64) {
+        staged_epilogue<8>(P, rc, nt, t_row, staging + (uint32_t)(warp - 2) * (32u * 128u), lane, grp);
+      } else {
+      for (int c = grp * 32; c < P.BN; c += 64) {
         uint32_t v[32];
         if (c + 32 <= P.BN) {
           tmem_ld32(t_row + (uint32_t)c, v);
@@ -344,6 +452,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld_wait();
           epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -412,7 +521,13 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
   P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
   const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
-  P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048) / stage_bytes));
+  P.stage_cols = 0;
+  if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
+    if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
+  }
+  const int staging_bytes = P.stage_cols ? TC_STAGING_BYTES + 128 : 0;
+  P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
+  if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
   P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -440,7 +555,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d (Cs=%d rows=%d BN=%d)", (int)r, p.Cs, p.ntaps * p.Np, P.BN);
   }
-  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024;
+  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024 + staging_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
