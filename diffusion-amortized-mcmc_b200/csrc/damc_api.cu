@@ -64,6 +64,8 @@ int MlpPack::refill(cudaStream_t s) {
   DAMC_CUDA(cudaMemcpyAsync(b2, src[3], sizeof(float) * ndf, k, s));
   DAMC_CUDA(cudaMemcpyAsync(w3, src[4], sizeof(float) * ndf, k, s));
   DAMC_CUDA(cudaMemcpyAsync(b3, src[5], sizeof(float), k, s));
+  DAMC_TRY(launch_transpose(W1, W1T, ndf, nz, s));
+  DAMC_TRY(launch_transpose(W2, W2T, ndf, ndf, s));
   return DAMC_OK;
 }
 
@@ -115,7 +117,7 @@ int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const flo
   cudaStream_t s = (cudaStream_t)stream;
   MlpPack* m = new MlpPack();
   m->kind = H_MLP; m->nz = nz; m->ndf = ndf; m->slope = negative_slope;
-  const size_t n = (size_t)ndf * nz + ndf + (size_t)ndf * ndf + ndf + ndf + 1;
+  const size_t n = 2 * ((size_t)ndf * nz + (size_t)ndf * ndf) + 3 * (size_t)ndf + 1;
   if (cudaMalloc(&m->slab, n * sizeof(float)) != cudaSuccess) { delete m; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_mlp: cudaMalloc failed"); }
   float* p = m->slab;
   m->W1 = p; p += (size_t)ndf * nz;
@@ -123,7 +125,9 @@ int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const flo
   m->W2 = p; p += (size_t)ndf * ndf;
   m->b2 = p; p += ndf;
   m->w3 = p; p += ndf;
-  m->b3 = p;
+  m->b3 = p; p += 1;
+  m->W1T = p; p += (size_t)ndf * nz;
+  m->W2T = p;
   const float* srcs[6] = {W1, b1, W2, b2, W3, b3};
   for (int i = 0; i < 6; ++i) m->src[i] = srcs[i];
   const int r = m->refill(s);
@@ -208,8 +212,8 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
     float* tr = trace ? trace + 4 * (size_t)i : nullptr;
     DAMC_TRY(generator_forward(g, ws, z, B, x, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, s));
     DAMC_TRY(generator_dgrad(g, ws, B, s));
-    DAMC_TRY(launch_ebm_langevin(m, z, B, 1, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr,
-                                 seed, chain0, step0 + (uint64_t)i, tr, 4, ws.dz_part, S, g->nz_p, g->nz, s));
+    DAMC_TRY(launch_ebm_step(m, z, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
+                             chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p, g->nz, s));
   }
   return DAMC_OK;
 }

@@ -16,6 +16,7 @@ struct MlpPack : damc_handle {
   int nz = 0, ndf = 0;
   float slope = 0.2f;
   float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  float *W1T = nullptr, *W2T = nullptr;  // transposed copies [nz][ndf], [ndf][ndf] for the single-step kernel
   const float* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller's tensors (for damc_repack)
   float* slab = nullptr;
   ~MlpPack() override { if (slab) cudaFree(slab); }
@@ -26,11 +27,17 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
                         uint64_t seed, uint64_t chain0, uint64_t step0, float* trace, int trace_stride,
                         const float* gpart, int nsplit, int gstride, int nz_if_no_ebm, cudaStream_t stream);
 
+// single Langevin step for many chains with the MLP streamed from L2 (the posterior sampler's per-step tail)
+int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
+                    uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
+                    int nz_if_no_ebm, cudaStream_t stream);
+int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
+
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
 // Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]
 // with m = (b,y,x) on an Hm x Wm grid, and A_t[m,:] = src[plane_t][b, y+dy_t, x+dx_t, :] (zero outside the grid).
 enum LayerType { L_FIRST = 0, L_UP = 1, L_SAME = 2 };  // 1x1->kxk (s1,p0) | k4,s2,p1 | k3,s1,p1
-enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3 };
+enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3, EPI_STORE_F32 = 4 };
 
 struct Tap { signed char plane, dy, dx, pad; };
 
@@ -52,8 +59,8 @@ struct Epilogue {
   float* loss;          // null or scalar accumulator: sum (xhat-x)^2 * inv_sigma2/2
   void* gcol;           // im2col'd dL/dh_last for the last layer's dgrad: [B*Hi*Wi][64], slot (kh*k+kw)*4 + c
   int nc, k, stride, padding, Hi, Wi, Ho, Wo;
-  // EPI_DGRAD_Z
-  int nz_out;           // row stride of the fp32 partial-sum output [split][B][nz_out]
+  // EPI_DGRAD_Z / EPI_STORE_F32
+  int nz_out;           // row stride of the fp32 output: [split][B][nz_out] partial sums, or [M][nz_out] raw accumulators
 };
 
 struct GemmPlan {
@@ -78,6 +85,10 @@ struct GenLayer {
   void* w_dgrad = nullptr;
   void* w_fwd_tc[4] = {nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tcgen05 engine (bf16 mode)
   void* w_dgrad_tc = nullptr;
+  // last layer, "scatter form": Y[m_in, (kh,kw,co)] = a[m_in,:] . W[:,co,kh,kw]  (one tap, N = k*k*nc), then col2im
+  void* w_scatter = nullptr;
+  void* w_scatter_tc = nullptr;
+  int n_sc = 0, np_sc = 0;
   int n_fwd = 0, np_fwd = 0;    // N / padded N of the forward GEMM
   int n_dg = 0, np_dg = 0;      // N / padded N of the dgrad GEMM
 };
@@ -90,6 +101,7 @@ struct GenPack : damc_handle {
   std::vector<damc_convt_layer> src;  // caller's tensors (for damc_repack)
   std::vector<void*> allocs;
   int dz_splits = 1;
+  bool last_scatter = false;  // last layer runs as scatter-form GEMM + per-image finish kernel (image fits in smem)
   bool use_tc = false;      // bf16 mode: tcgen05 engine (default) or the SIMT engine on bf16 storage (DAMC_TC=0)
   ~GenPack() override { for (void* p : allocs) cudaFree(p); }
   int refill(cudaStream_t stream) override;
@@ -100,6 +112,7 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
   std::vector<void*> act;    // a_1..a_{L-1}       T (NHWC)
   std::vector<void*> grad;   // g_1..g_{L-1}       T (planar for L_UP producers, flat for L_FIRST)
   void* gcol;                // [B*Hi*Wi][64]      T
+  float* ybuf;               // [B*Hi*Wi][np_sc]   fp32 (scatter-form last layer) or null
   float* dz_part;            // [splits][B][nz_p]  fp32
   size_t bytes;
 };
@@ -114,9 +127,12 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream);
 int tc_available();
 
 // weight packing -- gen_pack.cu
-enum PackMode { PK_FIRST_FWD, PK_FIRST_DGRAD, PK_UP_FWD, PK_UP_DGRAD, PK_SAME_FWD, PK_LAST_DGRAD_COL };
+enum PackMode { PK_FIRST_FWD, PK_FIRST_DGRAD, PK_UP_FWD, PK_UP_DGRAD, PK_SAME_FWD, PK_LAST_DGRAD_COL, PK_LAST_FWD_SCATTER };
 int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int pad, int mode, int cls, int ntaps,
                       int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream);
+size_t last_finish_smem(const GenLayer& y);
+int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
+                       float inv_sigma2, float* loss, void* gcol, cudaStream_t stream);
 int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int precision, cudaStream_t stream);
 
 // generator driver -- gen_driver.cu

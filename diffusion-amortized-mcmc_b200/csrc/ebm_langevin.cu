@@ -113,13 +113,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) ebm_langevin
 
   // ---- one-time: weights -> smem (zero padded), z tile -> smem ---------------------------------------------------
   if (a.use_ebm) {
-    for (int i = tid; i < HJ * S1; i += blockDim.x) {
-      const int r = i / S1, c = i - r * S1;
-      sW1[i] = (r < hj && c < nz) ? a.W1[(size_t)(j0 + r) * nz + c] : 0.f;
-    }
-    for (int i = tid; i < ndf * S2; i += blockDim.x) {
-      const int r = i / S2, c = i - r * S2;
-      sW2[i] = (c < hj) ? a.W2[(size_t)r * ndf + j0 + c] : 0.f;
+    {
+      const int wid = tid >> 5, ln = tid & 31, nw = blockDim.x >> 5;
+      for (int r = wid; r < HJ; r += nw) {  // one warp per row; the column loop unrolls into independent loads
+        const float* src = a.W1 + (size_t)(j0 + r) * nz;
+#pragma unroll 4
+        for (int c = ln; c < S1; c += 32) sW1[r * S1 + c] = (r < hj && c < nz) ? __ldg(src + c) : 0.f;
+      }
+      for (int r = wid; r < ndf; r += nw) {
+        const float* src = a.W2 + (size_t)r * ndf + j0;
+#pragma unroll 4
+        for (int c = ln; c < S2; c += 32) sW2[r * S2 + c] = (c < hj) ? __ldg(src + c) : 0.f;
+      }
     }
     for (int i = tid; i < HJ; i += blockDim.x) sb1[i] = i < hj ? a.b1[j0 + i] : 0.f;
     for (int i = tid; i < ndf; i += blockDim.x) { sb2[i] = a.b2[i]; sw3[i] = a.w3[i]; }
@@ -360,6 +365,183 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
   ebm_langevin_kernel<kChains><<<2 * clusters, 256, P.total, stream>>>(a);
   DAMC_CUDA(cudaGetLastError());
   count_launch();
+  return DAMC_OK;
+}
+
+// ---- single step, many chains: weights streamed from L2 (both orientations), chains tiled CH per CTA -----------------------
+// Used as the tail of every posterior Langevin step (reference MCMC.py:57-64): with K = 1 there is nothing to amortise a
+// 131 KB shared-memory fill over, so thread j walks column j of the transposed weights with coalesced loads instead.
+struct EbmStepArgs {
+  const float *W1, *W1T, *b1, *W2, *W2T, *b2, *w3, *b3;
+  int nz, ndf, use_ebm;
+  float slope;
+  float* z;
+  int B;
+  float step;
+  int with_noise;
+  const float* noise;  // [B,nz] for this step or null
+  uint64_t seed, chain0, step_index;
+  float* trace;        // null or [4]: sum E, (llhd), |z|^2/2, mean grad
+  const float* gpart;
+  int nsplit, gstride;
+  float inv_count;
+};
+
+// acc[c] += sum_i W[i*ld + col] * vec[i*CH + c], with the weight loads issued 8 at a time (L2 latency overlap)
+template <int CH>
+__device__ __forceinline__ void stream_matvec(const float* __restrict__ Wcol, int ld, int n, const float* vec, float (&acc)[CH]) {
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(Wcol + (size_t)(i + u) * ld);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int c4 = 0; c4 < CH / 4; ++c4) {
+        const float4 v = *reinterpret_cast<const float4*>(vec + (i + u) * CH + 4 * c4);
+        acc[4 * c4] = fmaf(w[u], v.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(w[u], v.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(w[u], v.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(w[u], v.w, acc[4 * c4 + 3]);
+      }
+    }
+  }
+  for (; i < n; ++i) {
+    const float w = __ldg(Wcol + (size_t)i * ld);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = fmaf(w, vec[i * CH + c], acc[c]);
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int nz = a.nz, ndf = a.ndf, tid = threadIdx.x;
+  float* zs = sm;                    // [nz][CH]
+  float* a1s = zs + nz * CH;         // [ndf][CH]
+  float* d2s = a1s + ndf * CH;       // [ndf][CH]
+  float* d1s = d2s + ndf * CH;       // [ndf][CH]
+  __shared__ float red[3];
+  const int c0 = blockIdx.x * CH;
+  const int nvalid = min(CH, a.B - c0);
+  if (tid < 3) red[tid] = 0.f;
+  for (int i = tid; i < nz * CH; i += blockDim.x) {
+    const int c = i / nz, k = i - c * nz;  // coalesced over k
+    zs[k * CH + c] = c < nvalid ? a.z[(size_t)(c0 + c) * nz + k] : 0.f;
+  }
+  __syncthreads();
+  float gE[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) gE[c] = 0.f;
+  if (a.use_ebm) {
+    float acc[CH];
+    unsigned m1 = 0u;
+    if (tid < ndf) {
+      const float bb = a.b1[tid];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = bb;
+      stream_matvec<CH>(a.W1T + tid, ndf, nz, zs, acc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if (acc[c] > 0.f) m1 |= 1u << c;
+        a1s[tid * CH + c] = acc[c] > 0.f ? acc[c] : a.slope * acc[c];
+      }
+    }
+    __syncthreads();
+    if (tid < ndf) {
+      const float bb = a.b2[tid], w3 = a.w3[tid];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = bb;
+      stream_matvec<CH>(a.W2T + tid, ndf, ndf, a1s, acc);
+      float e_part = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        d2s[tid * CH + c] = (acc[c] > 0.f ? 1.f : a.slope) * w3;
+        if (c < nvalid) e_part += w3 * (acc[c] > 0.f ? acc[c] : a.slope * acc[c]);
+      }
+      if (a.trace != nullptr) atomicAdd(&red[0], e_part);
+    }
+    __syncthreads();
+    if (tid < ndf) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      stream_matvec<CH>(a.W2 + tid, ndf, ndf, d2s, acc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d1s[tid * CH + c] = ((m1 >> c) & 1u) ? acc[c] : a.slope * acc[c];
+    }
+    __syncthreads();
+    if (tid < nz) {
+      stream_matvec<CH>(a.W1 + tid, nz, ndf, d1s, gE);
+    }
+  }
+  // fused update: thread k owns latent dimension k of the CH chains
+  float zsq = 0.f, gsum = 0.f;
+  if (tid < nz) {
+    const float half_s2 = 0.5f * a.step * a.step;
+    for (int c = 0; c < nvalid; ++c) {
+      const size_t chain = (size_t)(c0 + c);
+      float g = gE[c];
+      if (a.gpart != nullptr)
+        for (int s = 0; s < a.nsplit; ++s) g += a.gpart[((size_t)s * a.B + chain) * a.gstride + tid];
+      const float zv = zs[tid * CH + c];
+      const float grad = g + zv;
+      float nrm = 0.f;
+      if (a.with_noise)
+        nrm = a.noise ? a.noise[chain * nz + tid] : philox_normal1(a.seed, a.chain0 + chain, a.step_index, (uint32_t)tid);
+      a.z[chain * nz + tid] = zv - half_s2 * grad + a.step * nrm;
+      zsq += zv * zv;
+      gsum += grad;
+    }
+  }
+  if (a.trace != nullptr) {
+    zsq = warp_sum(zsq);
+    gsum = warp_sum(gsum);
+    if ((tid & 31) == 0) { atomicAdd(&red[1], zsq); atomicAdd(&red[2], gsum); }
+    __syncthreads();
+    if (tid == 0) {
+      if (a.use_ebm) atomicAdd(&a.trace[0], red[0] + (float)nvalid * a.b3[0]);
+      atomicAdd(&a.trace[2], 0.5f * red[1]);
+      atomicAdd(&a.trace[3], red[2] * a.inv_count);
+    }
+  }
+}
+
+int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
+                    uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
+                    int nz_if_no_ebm, cudaStream_t stream) {
+  constexpr int CH = 8;
+  EbmStepArgs a{};
+  a.use_ebm = m != nullptr;
+  if (m) {
+    a.W1 = m->W1; a.W1T = m->W1T; a.b1 = m->b1; a.W2 = m->W2; a.W2T = m->W2T; a.b2 = m->b2; a.w3 = m->w3; a.b3 = m->b3;
+    a.nz = m->nz; a.ndf = m->ndf; a.slope = m->slope;
+  } else {
+    a.nz = nz_if_no_ebm; a.ndf = 0; a.slope = 1.f;
+  }
+  if (a.nz < 1 || a.nz > 256 || a.ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM step kernel: nz <= 256 and ndf <= 256 (nz=%d ndf=%d)", a.nz, a.ndf);
+  a.z = z; a.B = B; a.step = step; a.with_noise = with_noise; a.noise = noise; a.seed = seed; a.chain0 = chain0;
+  a.step_index = step_index; a.trace = trace4; a.gpart = gpart; a.nsplit = nsplit; a.gstride = gstride;
+  a.inv_count = 1.0f / ((float)B * (float)a.nz);
+  const size_t smem = sizeof(float) * CH * ((size_t)a.nz + 3 * (size_t)a.ndf);
+  ebm_step_kernel<CH><<<ceil_div(B, CH), 256, smem, stream>>>(a);
+  DAMC_CUDA(cudaGetLastError());
+  count_launch();
+  return DAMC_OK;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    if (x < cols && y0 + r < rows) t[r][threadIdx.x] = src[(size_t)(y0 + r) * cols + x];
+  __syncthreads();
+  const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    if (ox < rows && oy0 + r < cols) dst[(size_t)(oy0 + r) * rows + ox] = t[threadIdx.x][r];
+}
+
+int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
+  transpose_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
+  DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
 

@@ -116,6 +116,22 @@ int GenPack::refill(cudaStream_t stream) {
       DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 1,
                                  precision, y.w_dgrad_tc, stream));
     }
+    if (last) {  // scatter-form operands: one tap, N = k*k*nc
+      y.n_sc = s.k * s.k * s.cout;
+      y.np_sc = (int)align_up(y.n_sc, 16);
+      const char* env = getenv("DAMC_LAST_SCATTER");
+      g->last_scatter = last_finish_smem(y) <= 200 * 1024 && !(env && env[0] == '0');
+      if (g->last_scatter) {
+        if (!y.w_scatter) DAMC_TRY(dev_alloc(g, &y.w_scatter, es * (size_t)y.cin * y.np_sc));
+        DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, PK_LAST_FWD_SCATTER, 0, 1, y.cin,
+                                   y.np_sc, 0, precision, y.w_scatter, stream));
+        if (use_tc) {
+          if (!y.w_scatter_tc) DAMC_TRY(dev_alloc(g, &y.w_scatter_tc, es * (size_t)y.cin * y.np_sc));
+          DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, PK_LAST_FWD_SCATTER, 0, 1, y.cin,
+                                     y.np_sc, 1, precision, y.w_scatter_tc, stream));
+        }
+      }
+    }
   }
   return DAMC_OK;
 }
@@ -136,6 +152,7 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   }
   const GenLayer& last = g->layers[L - 1];
   ws->gcol = take(es * (size_t)B * last.Hin * last.Win * 64);
+  ws->ybuf = g->last_scatter ? (float*)take(sizeof(float) * (size_t)B * last.Hin * last.Win * last.np_sc) : nullptr;
   ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(g, B) * B * g->nz_p);
   ws->bytes = o;
   return DAMC_OK;
@@ -178,6 +195,17 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     e.slope = g->slope;
     e.bias = y.bias;
     e.sy = e.sx = y.type == L_UP ? 2 : 1;
+    if (last && g->last_scatter) {
+      p.N = y.n_sc; p.Np = y.np_sc;
+      p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
+      p.W = y.w_scatter; p.Wtc = y.w_scatter_tc;
+      e.kind = EPI_STORE_F32;
+      e.out = ws.ybuf; e.nz_out = y.np_sc;
+      DAMC_TRY(run_gemm(g, p, stream));
+      DAMC_TRY(launch_last_finish(y, g->precision, ws.ybuf, B, x, xhat, 1.0f / (sigma * sigma), loss, ws.gcol, stream));
+      count_launch();
+      continue;
+    }
     if (last) {
       e.kind = EPI_FWD_LAST;
       e.x = x; e.xhat = xhat; e.loss = loss; e.gcol = ws.gcol;

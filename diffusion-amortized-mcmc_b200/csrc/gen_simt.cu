@@ -12,6 +12,8 @@
 //   k4,s2,p1 dgrad   : 16 taps over the 4 parity planes of dL/dh, stored plane-major             (K = 16 Cout)
 //   1x1 -> kxk first layer: a plain GEMM in both directions; last layer (Cout = nc): forward writes dL/dh already
 //   im2col'd ("gcol", 64 columns per input pixel) so its dgrad is a plain K=64 GEMM too.
+#include <algorithm>
+
 #include "damc_common.cuh"
 #include "damc_internal.h"
 #include "gen_epilogue.cuh"
@@ -168,6 +170,10 @@ __device__ __forceinline__ long long pack_src_index(int mode, int cls, int t, in
     } break;
     case PK_UP_DGRAD: { kh = t >> 2; kw = t & 3; co = c; ci = n; } break;
     case PK_SAME_FWD: { kh = t / 3; kw = t % 3; ci = c; co = n; } break;
+    case PK_LAST_FWD_SCATTER: {  // c = ci ; n = (kh*k+kw)*cout + co
+      ci = c; co = n % cout; const int s = n / cout; kh = s / k; kw = s % k;
+      if (s >= k * k) return -1;
+    } break;
     case PK_LAST_DGRAD_COL: {  // c = (kh*k+kw)*4 + ch ; n = ci
       const int s = c >> 2; co = c & 3; ci = n; kh = s / k; kw = s % k;
       if (s >= k * k) return -1;
@@ -201,6 +207,170 @@ int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int 
   else
     pack_convt_kernel<float><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
                                                          reinterpret_cast<float*>(dst));
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+// ---- last layer, scatter form: col2im + bias + tanh + likelihood gradient + im2col'd dL/dh ----------------------------------
+// Y[b][m_in][(kh*k+kw)*nc + co] holds the per-input-pixel contributions of ConvTranspose2d (reference diffusion_net.py:
+// 42-46); out[oy,ox,co] = bias + sum over (kh,kw) with (oy+p-kh, ox+p-kw) divisible by the stride and inside the input.
+// One CTA owns a block of IRB input rows of one image: it needs dL/dh on the output rows those inputs touch (a one-row
+// halo, recomputed) and Y on the input rows that feed those outputs (a further halo) -- all staged in shared memory.
+struct FinishArgs {
+  const float* Y; const float* bias; const float* x; float* xhat; float* loss; void* gcol;
+  int Hi, Wi, Ho, Wo, k, stride, pad, nc, np, irb, nblk;
+  float inv_sigma2;
+};
+
+struct FinishRange { int iy0, iy1, oa, ob, ia, ib; };
+__host__ __device__ inline int fdiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }   // floor(a/b), b > 0
+__host__ __device__ inline FinishRange finish_range(int blk, int irb, int Hi, int Ho, int k, int s, int p) {
+  FinishRange r;
+  r.iy0 = blk * irb;
+  r.iy1 = r.iy0 + irb < Hi ? r.iy0 + irb : Hi;
+  const int oa = r.iy0 * s - p, ob = (r.iy1 - 1) * s - p + k - 1;
+  r.oa = oa < 0 ? 0 : oa;
+  r.ob = ob > Ho - 1 ? Ho - 1 : ob;
+  const int ia = fdiv(r.oa + p - k + 1 + s - 1, s), ib = fdiv(r.ob + p, s);   // ceil / floor
+  r.ia = ia < 0 ? 0 : ia;
+  r.ib = ib > Hi - 1 ? Hi - 1 : ib;
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs a) {
+  extern __shared__ __align__(16) float fsm[];
+  const int b = blockIdx.x / a.nblk, blk = blockIdx.x - b * a.nblk, tid = threadIdx.x;
+  const FinishRange R = finish_range(blk, a.irb, a.Hi, a.Ho, a.k, a.stride, a.pad);
+  const int nyr = (R.ib - R.ia + 1) * a.Wi, ngr = (R.ob - R.oa + 1) * a.Wo;
+  const int pitch = a.np + 1;                   // odd pitch: consecutive pixels (threads) fall into different banks
+  float* Ys = fsm;                              // [(ib-ia+1)*Wi][np+1]
+  float* gS = fsm + (((size_t)nyr * pitch + 3) & ~(size_t)3);   // [(ob-oa+1)*Wo][4]
+  __shared__ float red[8];
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.Y + ((size_t)b * a.Hi + R.ia) * a.Wi * a.np);
+    const int q4 = a.np / 4;
+    for (int i = tid; i < nyr * q4; i += blockDim.x) {
+      const float4 v = __ldg(src + i);
+      const int row = i / q4, c4 = (i - row * q4) * 4;
+      float* d = Ys + (size_t)row * pitch + c4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  }
+  __syncthreads();
+  const int own0 = R.iy0 * a.stride, own1 = R.iy1 * a.stride;  // output rows this block reports (x_hat, loss)
+  float loss_acc = 0.f;
+  for (int pix = tid; pix < ngr; pix += blockDim.x) {
+    const int oyl = pix / a.Wo, ox = pix - oyl * a.Wo, oy = R.oa + oyl;
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < a.nc; ++c) h[c] = a.bias[c];
+    for (int kh = 0; kh < a.k; ++kh) {
+      const int ny = oy + a.pad - kh;
+      if (ny < 0 || ny % a.stride) continue;
+      const int iy = ny / a.stride;
+      if (iy >= a.Hi) continue;
+      for (int kw = 0; kw < a.k; ++kw) {
+        const int nx = ox + a.pad - kw;
+        if (nx < 0 || nx % a.stride) continue;
+        const int ix = nx / a.stride;
+        if (ix >= a.Wi) continue;
+        const float* yr = Ys + (size_t)((iy - R.ia) * a.Wi + ix) * pitch + (kh * a.k + kw) * a.nc;
+        for (int c = 0; c < a.nc; ++c) h[c] += yr[c];
+      }
+    }
+    const bool own = oy >= own0 && oy < own1;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < a.nc; ++c) {
+      const float xh = tanhf(h[c]);
+      const size_t xi = (((size_t)b * a.nc + c) * a.Ho + oy) * a.Wo + ox;
+      if (a.xhat && own) a.xhat[xi] = xh;
+      if (a.x) {
+        const float r = xh - a.x[xi];
+        g[c] = r * a.inv_sigma2 * (1.f - xh * xh);
+        if (own) loss_acc += 0.5f * a.inv_sigma2 * r * r;
+      }
+    }
+    *reinterpret_cast<float4*>(gS + (size_t)pix * 4) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  if (a.x == nullptr) return;
+  if (a.loss != nullptr) {
+    loss_acc = warp_sum(loss_acc);
+    if ((tid & 31) == 0) red[tid >> 5] = loss_acc;
+  }
+  __syncthreads();
+  if (a.loss != nullptr && tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    if (t != 0.f) atomicAdd(a.loss, t);
+  }
+  // im2col'd gradient rows for the last layer's dgrad: gcol[m_in][(kh*k+kw)*4 + c] = g[(iy*s-p+kh, ix*s-p+kw)][c]
+  constexpr int EPC = 16 / (int)sizeof(T);   // entries per 16-byte chunk (8 bf16 | 4 fp32)
+  constexpr int CH = 64 / EPC;               // chunks per 64-entry row
+  T* gc = reinterpret_cast<T*>(a.gcol) + ((size_t)b * a.Hi + R.iy0) * a.Wi * 64;
+  const int nrows = (R.iy1 - R.iy0) * a.Wi;
+  for (int i = tid; i < nrows * CH; i += blockDim.x) {
+    const int m = i / CH, j = i - m * CH;
+    const int iy = R.iy0 + m / a.Wi, ix = m % a.Wi;
+    float vals[EPC];
+#pragma unroll
+    for (int s2 = 0; s2 < EPC / 4; ++s2) {
+      const int slot = j * (EPC / 4) + s2;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (slot < a.k * a.k) {
+        const int kh = slot / a.k, kw = slot - kh * a.k;
+        const int oy = iy * a.stride - a.pad + kh, ox = ix * a.stride - a.pad + kw;
+        if (oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo)
+          gv = *reinterpret_cast<const float4*>(gS + (size_t)((oy - R.oa) * a.Wo + ox) * 4);
+      }
+      vals[4 * s2] = gv.x; vals[4 * s2 + 1] = gv.y; vals[4 * s2 + 2] = gv.z; vals[4 * s2 + 3] = gv.w;
+    }
+    T* dst = gc + (size_t)m * 64 + j * EPC;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(vals[2 * q], vals[2 * q + 1]);
+        w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+static size_t finish_smem_for(const GenLayer& y, int irb) {
+  size_t mx = 0;
+  const int nblk = ceil_div(y.Hin, irb);
+  for (int blk = 0; blk < nblk; ++blk) {
+    const FinishRange R = finish_range(blk, irb, y.Hin, y.Hout, y.k, y.stride, y.pad);
+    mx = std::max(mx, sizeof(float) * ((size_t)(R.ib - R.ia + 1) * y.Win * (y.np_sc + 1) + 4 + (size_t)(R.ob - R.oa + 1) * y.Wout * 4));
+  }
+  return mx;
+}
+static int finish_irb(const GenLayer& y) {  // input rows per CTA: ~4+ blocks per image, <= 56 KB so that 4 CTAs share an SM
+  int irb = std::max(1, y.Hin / 4);
+  while (irb > 1 && finish_smem_for(y, irb) > 56 * 1024) --irb;
+  return irb;
+}
+size_t last_finish_smem(const GenLayer& y) { return finish_smem_for(y, finish_irb(y)); }
+
+int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
+                       float inv_sigma2, float* loss, void* gcol, cudaStream_t stream) {
+  FinishArgs a{};
+  a.Y = Y; a.bias = y.bias; a.x = x; a.xhat = xhat; a.loss = loss; a.gcol = gcol;
+  a.Hi = y.Hin; a.Wi = y.Win; a.Ho = y.Hout; a.Wo = y.Wout; a.k = y.k; a.stride = y.stride; a.pad = y.pad;
+  a.nc = y.cout; a.np = y.np_sc; a.inv_sigma2 = inv_sigma2;
+  a.irb = finish_irb(y);
+  a.nblk = ceil_div(y.Hin, a.irb);
+  const size_t smem = finish_smem_for(y, a.irb);
+  if (precision == DAMC_PREC_BF16) {
+    DAMC_CUDA(cudaFuncSetAttribute(last_finish_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    last_finish_kernel<__nv_bfloat16><<<B * a.nblk, 256, smem, stream>>>(a);
+  } else {
+    DAMC_CUDA(cudaFuncSetAttribute(last_finish_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    last_finish_kernel<float><<<B * a.nblk, 256, smem, stream>>>(a);
+  }
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }

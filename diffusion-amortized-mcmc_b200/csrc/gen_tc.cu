@@ -23,9 +23,9 @@
 
 namespace damc {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
+constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
-constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 32 * 64 * 2;  // per epilogue warp: 32 rows x 64 bf16
+constexpr int TC_STAGING_PER_WARP = 32 * 64 * 2;  // per epilogue warp: 32 rows x 64 bf16
 
 struct TcParams {
   GemmPlan plan;
@@ -155,7 +155,7 @@ struct RowCtx {
 __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, int split, int n0, const uint32_t raw[16],
                                             float& loss_acc) {
   const Epilogue& e = p.epi;
-  if (!r.ok || n0 >= p.N) return;
+  if (!r.ok || n0 >= p.Np) return;
   if (e.kind == EPI_FWD_ACT && n0 + 16 <= p.N) {
     const long long o = (long long)r.b * e.o_b + (long long)(r.y * e.sy + e.py) * e.o_y +
                         (long long)(r.x * e.sx + e.px) * e.o_x + n0;
@@ -204,6 +204,14 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
     }
     return;
   }
+  if (e.kind == EPI_STORE_F32 && n0 + 16 <= p.Np) {  // padded weight columns are zero, so storing all Np columns is exact
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (long long)r.m * e.nz_out + n0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dst[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                           __uint_as_float(raw[4 * q + 3]));
+    return;
+  }
 #pragma unroll 1
   for (int j = 0; j < 16; ++j)
     if (n0 + j < p.N)
@@ -211,60 +219,67 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
 }
 
 // ---- staged epilogue: TMEM -> registers -> (bias+LeakyReLU | mask) -> swizzled smem -> coalesced 16-byte row stores ------
-// CPR = 16-byte chunks per row segment (8: 64 columns, 16: 128 columns).  All global accesses are issued in unrolled
-// batches so that a warp keeps 32/CPR x 16 independent 16-byte requests in flight.
-template <int CPR>
-__device__ __forceinline__ void staged_epilogue(const TcParams& P, const RowCtx& rc, int nt, uint32_t t_row,
-                                                uint32_t my_stage, int lane, int grp) {
-  const GemmPlan& p = P.plan;
-  const Epilogue& e = p.epi;
-  constexpr int SW = CPR * 8, RPI = 32 / CPR, NIT = 32 / RPI;
-  constexpr uint32_t row_bytes = SW * 2;
-  const bool is_mask = e.kind == EPI_DGRAD_MASK;
-  const __nv_bfloat16* act_row = nullptr;
-  __nv_bfloat16* out_row = nullptr;
-  if (rc.ok) {
-    if (is_mask) {
-      act_row = reinterpret_cast<const __nv_bfloat16*>(e.act) + (long long)rc.m * p.N;
-      long long o;
-      if (e.planar_out) {
-        const int Hh = p.Hm >> 1, Wh = p.Wm >> 1;
-        o = (long long)((rc.y & 1) * 2 + (rc.x & 1)) * p.B * Hh * Wh * p.N +
-            (((long long)rc.b * Hh + (rc.y >> 1)) * Wh + (rc.x >> 1)) * p.N;
+// A warp owns 32 accumulator rows (its TMEM lane quarter) and walks 64-column segments.  Row segments are moved between
+// global memory and a per-warp XOR-swizzled smem tile so that 8 consecutive lanes cover one contiguous 128-byte piece of
+// a row (coalesced both ways).  For the mask epilogue the activation rows (sign source) are fetched into registers TWO
+// segments ahead -- across tile boundaries -- so that each lane keeps 16 independent 16-byte loads in flight.
+struct StagedEpi {
+  static constexpr int CPR = 8, SW = 64, RPI = 4, NIT = 8;
+  static constexpr uint32_t row_bytes = SW * 2;
+  unsigned long long out_bits;
+  int sub, j;
+
+  __device__ __forceinline__ static unsigned long long act_ptr_bits(const GemmPlan& p, const RowCtx& rc) {
+    return (unsigned long long)(reinterpret_cast<const __nv_bfloat16*>(p.epi.act) + (rc.ok ? (long long)rc.m * p.N : 0ll));
+  }
+  __device__ __forceinline__ void set_out(const GemmPlan& p, const RowCtx& rc) {
+    const Epilogue& e = p.epi;
+    __nv_bfloat16* out_row = nullptr;
+    if (rc.ok) {
+      if (e.kind == EPI_DGRAD_MASK) {
+        long long o;
+        if (e.planar_out) {
+          const int Hh = p.Hm >> 1, Wh = p.Wm >> 1;
+          o = (long long)((rc.y & 1) * 2 + (rc.x & 1)) * p.B * Hh * Wh * p.N +
+              (((long long)rc.b * Hh + (rc.y >> 1)) * Wh + (rc.x >> 1)) * p.N;
+        } else {
+          o = (long long)rc.m * p.N;
+        }
+        out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
       } else {
-        o = (long long)rc.m * p.N;
+        out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)rc.b * e.o_b +
+                  (long long)(rc.y * e.sy + e.py) * e.o_y + (long long)(rc.x * e.sx + e.px) * e.o_x;
       }
-      out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
-    } else {
-      out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)rc.b * e.o_b +
-                (long long)(rc.y * e.sy + e.py) * e.o_y + (long long)(rc.x * e.sx + e.px) * e.o_x;
+    }
+    out_bits = (unsigned long long)out_row;
+  }
+  // issue the 8 coalesced 16-byte loads of one 32-row x 64-column activation segment
+  __device__ __forceinline__ void request(uint4 (&r)[NIT], unsigned long long act_bits, int n_base) const {
+    // Unconditional loads: rows outside the problem read row 0 (their results are never stored).  A predicated load
+    // followed by a select would make every load wait for its own result and serialise the batch.
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const unsigned long long pb = __shfl_sync(0xffffffffu, act_bits, i * RPI + sub);
+      r[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pb) + n_base) + j);
     }
   }
-  const unsigned long long act_bits = (unsigned long long)act_row, out_bits = (unsigned long long)out_row;
-  const int sub = lane / CPR, j = lane % CPR;
-  for (int seg = grp * SW; seg < P.BN; seg += 2 * SW) {  // the two warps of a lane quarter alternate segments
-    const int n_base = nt * P.BN + seg;
-    if (n_base >= p.N) break;
-    if (is_mask) {  // coalesced, batched load of the activation rows (sign source) into the staging buffer
-      uint4 a[NIT];
+  __device__ __forceinline__ void stash(const uint4 (&r)[NIT], uint32_t my_stage) const {
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const unsigned long long pb = __shfl_sync(0xffffffffu, act_bits, i * RPI + sub);
-        a[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (pb) a[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pb) + n_base) + j);
-      }
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int R = i * RPI + sub;
-        const uint32_t dst = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a[i].x), "r"(a[i].y), "r"(a[i].z), "r"(a[i].w) : "memory");
-      }
-      __syncwarp();
+    for (int i = 0; i < NIT; ++i) {
+      const int R = i * RPI + sub;
+      const uint32_t dst = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[i].x), "r"(r[i].y), "r"(r[i].z), "r"(r[i].w) : "memory");
     }
+    __syncwarp();
+  }
+  // accumulators of one segment -> epilogue math -> smem -> global
+  __device__ __forceinline__ void process(const GemmPlan& p, uint32_t t_seg, uint32_t my_stage, int lane, int n_base) const {
+    const Epilogue& e = p.epi;
+    const bool is_mask = e.kind == EPI_DGRAD_MASK;
 #pragma unroll 1
     for (int c = 0; c < SW; c += 32) {
       uint32_t v[32];
-      tmem_ld32(t_row + (uint32_t)(seg + c), v);
+      tmem_ld32(t_seg + (uint32_t)c, v);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -276,10 +291,11 @@ __device__ __forceinline__ void staged_epilogue(const TcParams& P, const RowCtx&
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(aw[0]), "=r"(aw[1]), "=r"(aw[2]), "=r"(aw[3]) : "r"(addr) : "memory");
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
-            const uint32_t lo = aw[t2] & 0xffffu, hi = aw[t2] >> 16;
-            const float s0 = (lo != 0u && lo < 0x8000u) ? 1.f : e.slope;
-            const float s1 = (hi != 0u && hi < 0x8000u) ? 1.f : e.slope;
-            w[t2] = pack_bf16x2(__uint_as_float(v[8 * g + 2 * t2]) * s0, __uint_as_float(v[8 * g + 2 * t2 + 1]) * s1);
+            // two bf16 activations per word: "> 0" is a signed compare of each half (as int32: high half >= 0x10000)
+            float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
+            if ((int)(aw[t2] << 16) <= 0) g0 *= e.slope;
+            if ((int)aw[t2] < 0x10000) g1 *= e.slope;
+            w[t2] = pack_bf16x2(g0, g1);
           }
         } else {
           const float4* bp = reinterpret_cast<const float4*>(e.bias + ((n_base + c + 8 * g) % e.bias_mod));
@@ -298,7 +314,7 @@ __device__ __forceinline__ void staged_epilogue(const TcParams& P, const RowCtx&
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {  // write-out: CPR consecutive lanes cover one contiguous row segment
+    for (int i = 0; i < NIT; ++i) {  // write-out: 8 consecutive lanes cover one contiguous 128-byte row piece
       const int R = i * RPI + sub;
       const unsigned long long pb = __shfl_sync(0xffffffffu, out_bits, R);
       const uint32_t src = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
@@ -308,10 +324,13 @@ __device__ __forceinline__ void staged_epilogue(const TcParams& P, const RowCtx&
     }
     __syncwarp();
   }
-}
+};
 
 // ---- the kernel --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// EW = epilogue warps: 8 for MMA-bound launches; 16 (four per TMEM lane quarter) when K is so short that the epilogue
+// is the critical path and needs the extra issue slots.
+template <int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -333,7 +352,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
@@ -413,50 +432,110 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;  // two warps share a quarter and split the columns
-    int it = 0;
+    constexpr int NG = EW / 4;        // warps per lane quarter
+    const int grp = (warp - 2) >> 2;  // the NG warps of a quarter split the columns
     float loss_acc = 0.f;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int mt, nt, sp, b0, y0;
+    auto row_ctx = [&](int tile, int& nt, int& sp) {  // row of this thread inside the tile -> (chain, y, x) on the M grid
+      int mt, b0, y0;
       decode(tile, mt, nt, sp);
       tile_origin(mt, b0, y0);
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      // row of this thread inside the tile -> (chain, y, x) on the M grid
       const int r = q * 32 + lane;
       RowCtx rc;
-      {
-        const int per_img = P.Ht * p.Wm;
-        const int bt = r / per_img, rem = r - bt * per_img;
-        rc.b = b0 + bt;
-        rc.y = y0 + rem / p.Wm;
-        rc.x = rem % p.Wm;
-        rc.ok = r < P.tile_rows && rc.b < p.B && rc.y < p.Hm;
-        rc.m = (rc.b * p.Hm + rc.y) * p.Wm + rc.x;
-      }
-      mbar_wait(bar_tfull(as), aphase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
-      if (P.stage_cols == 64) {
-        staged_epilogue<8>(P, rc, nt, t_row, staging + (uint32_t)(warp - 2) * (32u * 128u), lane, grp);
+      const int per_img = P.Ht * p.Wm;
+      const int bt = r / per_img, rem = r - bt * per_img;
+      rc.b = b0 + bt;
+      rc.y = y0 + rem / p.Wm;
+      rc.x = rem % p.Wm;
+      rc.ok = r < P.tile_rows && rc.b < p.B && rc.y < p.Hm;
+      rc.m = (rc.b * p.Hm + rc.y) * p.Wm + rc.x;
+      return rc;
+    };
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (P.stage_cols == 64) {
+      // ---- staged path: flat software pipeline over (tile, segment) items of this warp ----
+      const bool is_mask = p.epi.kind == EPI_DGRAD_MASK;
+      const int nseg_w = (P.BN / 64 - grp + NG - 1) / NG;  // segments of a tile handled by this warp: grp, grp+NG, ...
+      const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (32u * 128u);
+      StagedEpi se;
+      se.sub = lane / StagedEpi::CPR;
+      se.j = lane % StagedEpi::CPR;
+      if (nseg_w == 0) {
+        for (int k = 0; k < ntl; ++k) {
+          mbar_wait(bar_tfull(k & 1), (uint32_t)(k >> 1) & 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(k & 1));
+        }
       } else {
-      for (int c = grp * 32; c < P.BN; c += 64) {
-        uint32_t v[32];
-        if (c + 32 <= P.BN) {
-          tmem_ld32(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
-          epi_chunk16(p, rc, sp, nt * P.BN + c + 16, v + 16, loss_acc);
-        } else {
-          tmem_ld16(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+        const int nitems = ntl * nseg_w;
+        uint4 ra[StagedEpi::NIT], rb[StagedEpi::NIT];
+        auto request = [&](uint4 (&r)[StagedEpi::NIT], int item) {
+          if (!is_mask || item >= nitems) return;
+          const int k = item / nseg_w, sg = item - k * nseg_w;
+          int nt, sp;
+          const RowCtx rc = row_ctx((int)blockIdx.x + k * (int)gridDim.x, nt, sp);
+          const int n_base = nt * P.BN + (grp + NG * sg) * 64;
+          if (n_base < p.N) se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
+        };
+        request(ra, 0);
+        request(rb, 1);
+        int nt = 0, sp = 0;
+        // one (tile, segment) item; r holds its activation rows (requested two items ago) and is re-armed for item+2.
+        // The two register sets alternate (no register copies: a copy would wait on the loads it moves).
+        auto do_item = [&](int item, uint4 (&r)[StagedEpi::NIT]) {
+          const int k = item / nseg_w, sg = item - k * nseg_w;
+          const int as = k & 1;
+          if (sg == 0) {
+            const RowCtx rc = row_ctx((int)blockIdx.x + k * (int)gridDim.x, nt, sp);
+            se.set_out(p, rc);
+          }
+          const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
+          if (is_mask) {
+            se.stash(r, my_stage);
+            request(r, item + 2);
+          }
+          if (sg == 0) {
+            mbar_wait(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
+            tc_fence_after();
+          }
+          if (n_base < p.N) se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base);
+          if (sg == nseg_w - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(as));
+          }
+        };
+        for (int item = 0; item < nitems; item += 2) {
+          do_item(item, ra);
+          if (item + 1 < nitems) do_item(item + 1, rb);
         }
       }
+    } else {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int nt, sp;
+        const RowCtx rc = row_ctx(tile, nt, sp);
+        const int as = it & 1;
+        mbar_wait(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = t_lane + (uint32_t)as * 256u;
+        for (int c = grp * 32; c < P.BN; c += 32 * NG) {
+          uint32_t v[32];
+          if (c + 32 <= P.BN) {
+            tmem_ld32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+            epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+            epi_chunk16(p, rc, sp, nt * P.BN + c + 16, v + 16, loss_acc);
+          } else {
+            tmem_ld16(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+            epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(as));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(as));
     }
     if (p.epi.kind == EPI_FWD_LAST && p.epi.loss != nullptr) {
       loss_acc = warp_sum(loss_acc);
@@ -525,7 +604,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
     if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
   }
-  const int staging_bytes = P.stage_cols ? TC_STAGING_BYTES + 128 : 0;
+  const int ew = (P.stage_cols && P.kb_per_split <= 4 && P.BN >= 256 && !getenv("DAMC_TC_EW8")) ? 16 : 8;
+  const int staging_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP + 128 : 0;
   P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
@@ -558,7 +638,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024 + staging_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -568,7 +649,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int total = P.m_tiles * P.n_tiles * p.ksplit;
-  convgemm_tc_kernel<<<std::min(total, num_sms), TC_THREADS, smem, stream>>>(tmA, tmB, P);
+  if (ew == 16) convgemm_tc_kernel<16><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(tmA, tmB, P);
+  else convgemm_tc_kernel<8><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(tmA, tmB, P);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
