@@ -213,6 +213,12 @@ def run_ours(args):
         gemm_flops = B * L_STEPS * args.steps * FLOP_PER_CHAIN_STEP  # this rank's GEMM launches
         achieved = gemm_flops / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else None
         cpu_v, cpu_dt = (cpu_reference(args.cpu_chains, args.cpu_lsteps) if world == 1 and not args.no_cpu else (None, None))
+        traffic = None  # mean DRAM bytes per GEMM launch from the committed ncu capture of the same workload
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_B1024.json")
+        if os.path.exists(tpath) and args.precision == "bf16":
+            tj = json.load(open(tpath))
+            if tj.get("chains") == B:
+                traffic = tj["mean_dram_bytes_per_gemm_launch"]
         line = {
             "metric": "posterior Langevin chain-steps/sec (CIFAR-10 shape)", "value": value, "unit": "chain-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -228,7 +234,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": B * (NC * IMG * IMG + NZ) * 4, "d2h_bytes_per_step": B * NZ * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": traffic,
+                         "traffic_note": "mean dram__bytes_read+write per GEMM launch, profiles/r01_traffic_B1024.*",
                          "peak_source": pk["src"],
                          "kernel": "generator implicit-GEMM launches (%d per timed region, %.1f%% of step time)"
                                    % (gemm_n.value, 100.0 * gemm_ms.value / ms)},
@@ -252,7 +259,7 @@ def main():
     ap.add_argument("--chains", type=int, default=int(os.environ.get("DAMC_BENCH_CHAINS", "1024")),
                     help="chains per GPU")
     ap.add_argument("--cpu-chains", type=int, default=128)
-    ap.add_argument("--cpu-lsteps", type=int, default=3)
+    ap.add_argument("--cpu-lsteps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
