@@ -424,6 +424,12 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
   const int c0 = blockIdx.x * CH;
   const int nvalid = min(CH, a.B - c0);
   if (tid < 3) red[tid] = 0.f;
+  if (a.use_ebm) {  // pull the whole weight slab (W1 .. W2T are one allocation, ~0.5 MB) into L2 ahead of the mat-vecs
+    const char* base = reinterpret_cast<const char*>(a.W1);
+    const size_t bytes = (size_t)(a.W2T + (size_t)ndf * ndf - a.W1) * sizeof(float);
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)blockDim.x * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+  }
   for (int i = tid; i < nz * CH; i += blockDim.x) {
     const int c = i / nz, k = i - c * nz;  // coalesced over k
     zs[k * CH + c] = c < nvalid ? a.z[(size_t)(c0 + c) * nz + k] : 0.f;

@@ -249,12 +249,23 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs a) {
   __shared__ float red[8];
   {
     const float4* src = reinterpret_cast<const float4*>(a.Y + ((size_t)b * a.Hi + R.ia) * a.Wi * a.np);
-    const int q4 = a.np / 4;
-    for (int i = tid; i < nyr * q4; i += blockDim.x) {
-      const float4 v = __ldg(src + i);
-      const int row = i / q4, c4 = (i - row * q4) * 4;
-      float* d = Ys + (size_t)row * pitch + c4;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    const int q4 = a.np / 4, n4 = nyr * q4;
+    for (int i0 = tid; i0 < n4; i0 += 4 * blockDim.x) {  // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n4) {
+          const int row = i / q4, c4 = (i - row * q4) * 4;
+          float* d = Ys + (size_t)row * pitch + c4;
+          d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+        }
+      }
     }
   }
   __syncthreads();

@@ -477,8 +477,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int n_base = nt * P.BN + (grp + NG * sg) * 64;
           if (n_base < p.N) se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
         };
+        constexpr int AHEAD = EW == 8 ? 2 : 1;  // 16 warps: one register set each (keeps the kernel spill-free)
         request(ra, 0);
-        request(rb, 1);
+        if (AHEAD == 2) request(rb, 1);
         int nt = 0, sp = 0;
         // one (tile, segment) item; r holds its activation rows (requested two items ago) and is re-armed for item+2.
         // The two register sets alternate (no register copies: a copy would wait on the loads it moves).
@@ -492,7 +493,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
           if (is_mask) {
             se.stash(r, my_stage);
-            request(r, item + 2);
+            request(r, item + AHEAD);
           }
           if (sg == 0) {
             mbar_wait(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
@@ -505,9 +506,13 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (lane == 0) mbar_arrive(bar_tempty(as));
           }
         };
-        for (int item = 0; item < nitems; item += 2) {
-          do_item(item, ra);
-          if (item + 1 < nitems) do_item(item + 1, rb);
+        if (AHEAD == 2) {
+          for (int item = 0; item < nitems; item += 2) {
+            do_item(item, ra);
+            if (item + 1 < nitems) do_item(item + 1, rb);
+          }
+        } else {
+          for (int item = 0; item < nitems; ++item) do_item(item, ra);
         }
       }
     } else {

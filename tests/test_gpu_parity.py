@@ -308,3 +308,24 @@ def test_damc_sampler_golden(name, dev):
     err = relmax(z, z64)
     print(f"{name}: ours-vs-fp64 {err:.3e}   reference fp32-vs-fp64 {ref_err:.3e}")
     assert err < max(2.0 * ref_err, 1e-3), (err, ref_err)
+
+
+def test_toy_amortizer_golden(dev):
+    """_netQ_U_toy (reference toy_example/src/diffusion_net.py:141-239): nz = 2 latent, MLP encoder, T = 10."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    g = np.load(os.path.join(GOLDEN, "toy.npz"), allow_pickle=True)
+    B, T = int(g["cfg"][0]), 10
+    Q = dn._netQ_U(nc=3, nz=2, nxemb=128, ntemb=128, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
+                   logsnr_max=9.8, var_type="large", with_noise=True)
+    Q.encoder = torch.nn.Sequential(torch.nn.Linear(2, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                                    torch.nn.Linear(128, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128))
+    Q.load_state_dict(synth.module_state_like(Q, prefix="Qtoy."))
+    Q = Q.to(dev).eval()
+    x = synth.det_normal("toy.x", (B, 2)).to(dev)
+    zT, qn = synth.det_normal("toy.zT", (B, 2)), synth.det_normal("toy.qnoise", (T - 1, B, 2))
+    with torch.no_grad():
+        assert relmax(Q.encoder(x), g["q_xemb"]) < 1e-5
+    z = MCMC.damc_sample(Q, x=x, noise=qn.to(dev), z_init=zT)
+    err = relmax(z, g["q_z_f32"])
+    print(f"toy amortizer: ours-vs-reference-fp32 {err:.3e}")
+    assert err < 5e-3, err
