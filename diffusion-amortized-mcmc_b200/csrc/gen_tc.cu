@@ -130,6 +130,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cta_group::2 (CTA pair) variants ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive (once the issued MMAs have completed) on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major SWIZZLE_128B: 8-row groups of 128-byte rows, 1024 B apart (SBO); LBO unused.
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -329,7 +382,10 @@ struct StagedEpi {
 // ---- the kernel --------------------------------------------------------------------------------------------------------
 // EW = epilogue warps: 8 for MMA-bound launches; 16 (four per TMEM lane quarter) when K is so short that the epilogue
 // is the critical path and needs the extra issue slots.
-template <int EW>
+// CG = CTAs per MMA: 1, or 2 (cta_group::2: a CTA pair computes a 256 x 256 tile; each CTA stages its own 128 rows of
+// A and 128 of the 256 weight rows, so L2->smem traffic and B smem reads per FLOP drop by a third; the leader CTA's
+// MMA thread issues for both, commits multicast to both CTAs' barriers).
+template <int EW, int CG>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ TcParams P) {
@@ -348,27 +404,32 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // MMA unit (CTA or CTA pair)
+  const int nunits = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EW); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EW * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  if (warp == 1) { if (CG == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS); else tmem_alloc(tmem_slot, TC_TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const GemmPlan& p = P.plan;
-  const int total_tiles = P.m_tiles * P.n_tiles * p.ksplit;
+  const int m_units = (P.m_tiles + CG - 1) / CG;
+  const int total_tiles = m_units * P.n_tiles * p.ksplit;
 
   auto decode = [&](int tile, int& mt, int& nt, int& sp) {
     nt = tile % P.n_tiles;
     const int r = tile / P.n_tiles;
-    mt = r % P.m_tiles;
-    sp = r / P.m_tiles;
+    mt = (r % m_units) * CG + (int)cta_rank;   // this CTA's 128-row tile (may lie past the end: rows are masked)
+    sp = r / m_units;
   };
   auto tile_origin = [&](int mt, int& b0, int& y0) {
     if (P.Bt == 1) { b0 = mt / P.tiles_per_img; y0 = (mt - b0 * P.tiles_per_img) * P.Ht; }
@@ -380,7 +441,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
         int mt, nt, sp, b0, y0;
         decode(tile, mt, nt, sp);
         tile_origin(mt, b0, y0);
@@ -389,21 +450,29 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int t = kb / P.kb_per_tap, c0 = (kb - t * P.kb_per_tap) * TC_BK;
           const Tap tp = p.taps[t];
           mbar_wait(bar_empty(stage), phase ^ 1u);
-          mbar_expect_tx(bar_full(stage), P.a_box_bytes + P.b_box_bytes);
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          tma_load_5d(sa, &tmA, bar_full(stage), c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
-          tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, t * p.Np + nt * P.BN);
+          if (CG == 2) {
+            // both CTAs' loads report to the LEADER's full barrier, which expects the bytes of the whole pair
+            if (cta_rank == 0) mbar_expect_tx(bar_full(stage), 2u * (P.a_box_bytes + P.b_box_bytes));
+            const uint32_t lead_full = mapa_u32(bar_full(stage), 0u);
+            tma_load_5d_2sm(sa, &tmA, lead_full, c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
+            tma_load_2d_2sm(sa + TC_A_BYTES, &tmB, lead_full, c0, t * p.Np + nt * P.BN + (int)cta_rank * (P.BN / 2));
+          } else {
+            mbar_expect_tx(bar_full(stage), P.a_box_bytes + P.b_box_bytes);
+            tma_load_5d(sa, &tmA, bar_full(stage), c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
+            tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, t * p.Np + nt * P.BN);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
         int mt, nt, sp;
         decode(tile, mt, nt, sp);
         const int kb0 = sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
@@ -418,15 +487,17 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + TC_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(bar_empty(stage));  // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < TC_BK / 16; ++k) {  // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
+            if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (CG == 2) umma_commit_2sm(bar_empty(stage)); else umma_commit(bar_empty(stage));  // frees the smem slot
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
         if (kb1 <= kb0) {  // empty K range (trailing split): nothing was accumulated -> signal with zeros impossible;
           // the host guarantees kb_per_split * (ksplit-1) < kb_total, so this cannot happen
         }
-        umma_commit(bar_tfull(as));  // accumulator complete
+        if (CG == 2) umma_commit_2sm(bar_tfull(as)); else umma_commit(bar_tfull(as));  // accumulator complete
       }
     }
   } else {
@@ -455,7 +526,11 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ---- staged path: flat software pipeline over (tile, segment) items of this warp ----
       const bool is_mask = p.epi.kind == EPI_DGRAD_MASK;
       const int nseg_w = (P.BN / 64 - grp + NG - 1) / NG;  // segments of a tile handled by this warp: grp, grp+NG, ...
-      const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int ntl = (total_tiles - unit + nunits - 1) / nunits;
+      const uint32_t tempty_lead[2] = {CG == 2 ? mapa_u32(bar_tempty(0), 0u) : 0u, CG == 2 ? mapa_u32(bar_tempty(1), 0u) : 0u};
+      auto release_acc = [&](int as) {  // this warp is done with accumulator `as` (reported to the MMA-issuing CTA)
+        if (CG == 2) mbar_arrive_cluster(tempty_lead[as]); else mbar_arrive(bar_tempty(as));
+      };
       const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (32u * 128u);
       StagedEpi se;
       se.sub = lane / StagedEpi::CPR;
@@ -464,7 +539,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int k = 0; k < ntl; ++k) {
           mbar_wait(bar_tfull(k & 1), (uint32_t)(k >> 1) & 1u);
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty(k & 1));
+          if (lane == 0) release_acc(k & 1);
         }
       } else {
         const int nitems = ntl * nseg_w;
@@ -473,7 +548,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (!is_mask || item >= nitems) return;
           const int k = item / nseg_w, sg = item - k * nseg_w;
           int nt, sp;
-          const RowCtx rc = row_ctx((int)blockIdx.x + k * (int)gridDim.x, nt, sp);
+          const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
           const int n_base = nt * P.BN + (grp + NG * sg) * 64;
           if (n_base < p.N) se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
         };
@@ -487,7 +562,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int k = item / nseg_w, sg = item - k * nseg_w;
           const int as = k & 1;
           if (sg == 0) {
-            const RowCtx rc = row_ctx((int)blockIdx.x + k * (int)gridDim.x, nt, sp);
+            const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
             se.set_out(p, rc);
           }
           const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
@@ -503,7 +578,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (sg == nseg_w - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty(as));
+            if (lane == 0) release_acc(as);
           }
         };
         if (AHEAD == 2) {
@@ -517,7 +592,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     } else {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
         int nt, sp;
         const RowCtx rc = row_ctx(tile, nt, sp);
         const int as = it & 1;
@@ -539,7 +614,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(as));
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(bar_tempty(as), 0u)); else mbar_arrive(bar_tempty(as)); }
       }
     }
     if (p.epi.kind == EPI_FWD_LAST && p.epi.loss != nullptr) {
@@ -549,9 +624,10 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA may retire while the pair's MMAs / multicast arrives can still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS); else tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -603,18 +679,22 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: ksplit %d leaves an empty K range (%d blocks)", p.ksplit, P.kb_total);
   P.a_box_bytes = (uint32_t)P.tile_rows * TC_BK * 2;
   P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
-  P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
-  const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
   P.stage_cols = 0;
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
     if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
   }
   const int ew = (P.stage_cols && P.kb_per_split <= 4 && P.BN >= 256 && !getenv("DAMC_TC_EW8")) ? 16 : 8;
+  // CTA-pair MMA for the MMA-bound launches: full 256-wide N tiles, long K, an even grid of pairs
+  static const bool allow_2sm = []{ const char* e = getenv("DAMC_TC_2SM"); return !(e && e[0] == '0'); }();
+  const int cg = (allow_2sm && ew == 8 && P.BN == 256 && p.Np % 256 == 0 && P.kb_per_split >= 16 && P.m_tiles >= 2) ? 2 : 1;
+  if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
+  P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
+  const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
   const int staging_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP + 128 : 0;
   P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
 
   CUtensorMap tmA, tmB;
   {
@@ -633,7 +713,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   {
     const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)p.ntaps * p.Np};
     const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)P.BN};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(P.BN / cg)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -643,8 +723,9 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024 + staging_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -653,9 +734,23 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_CUDA(cudaGetDevice(&dev));
     DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (cg == 2) {
+    const int units = ceil_div(P.m_tiles, 2) * P.n_tiles * p.ksplit;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(units, num_sms / 2));
+    cfg.blockDim = dim3(64 + 32 * 8);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, tmA, tmB, P));
+    return DAMC_OK;
+  }
   const int total = P.m_tiles * P.n_tiles * p.ksplit;
-  if (ew == 16) convgemm_tc_kernel<16><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(tmA, tmB, P);
-  else convgemm_tc_kernel<8><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(tmA, tmB, P);
+  if (ew == 16) convgemm_tc_kernel<16, 1><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(tmA, tmB, P);
+  else convgemm_tc_kernel<8, 1><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(tmA, tmB, P);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
