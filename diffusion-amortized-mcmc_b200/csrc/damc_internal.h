@@ -73,6 +73,8 @@ struct GemmPlan {
   const void* Wtc;          // tcgen05 engine: [ntaps][Np][Cs] bf16 (K contiguous), or null
   int N, Np;                // logical / padded (multiple of 16) output columns
   int ksplit;               // >1: grid.z splits the K loop (EPI_DGRAD_Z only)
+  int ncls;                 // tcgen05 engine only: 4 = all output-parity classes of a k4-s2-p1 forward in ONE launch
+                            // (taps and epilogue parity derived from the class; Wtc holds the 4 class blocks back to back)
   Epilogue epi;
 };
 

@@ -97,7 +97,8 @@ int GenPack::refill(cudaStream_t stream) {
       DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
                                  precision, y.w_fwd[c], stream));
       if (use_tc) {
-        if (!y.w_fwd_tc[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd_tc[c], es * (size_t)ntaps * Cs * y.np_fwd));
+        if (!y.w_fwd_tc[0]) DAMC_TRY(dev_alloc(g, &y.w_fwd_tc[0], es * (size_t)ncls * ntaps * Cs * y.np_fwd));
+        y.w_fwd_tc[c] = (char*)y.w_fwd_tc[0] + es * (size_t)c * ntaps * Cs * y.np_fwd;  // class blocks back to back
         DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 1,
                                    precision, y.w_fwd_tc[c], stream));
       }
@@ -222,6 +223,11 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     if (y.type == L_FIRST) {
       p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
       p.W = y.w_fwd[0]; p.Wtc = y.w_fwd_tc[0];
+      DAMC_TRY(run_gemm(g, p, stream));
+    } else if (y.type == L_UP && g->use_tc && !last && !getenv("DAMC_TC_NOMERGE")) {
+      up_fwd_taps(0, p);           // (taps are derived from the class inside the kernel)
+      p.W = y.w_fwd[0]; p.Wtc = y.w_fwd_tc[0];
+      p.ncls = 4;
       DAMC_TRY(run_gemm(g, p, stream));
     } else if (y.type == L_UP) {
       for (int cls = 0; cls < 4; ++cls) {

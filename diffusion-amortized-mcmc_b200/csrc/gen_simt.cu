@@ -237,8 +237,11 @@ __host__ __device__ inline FinishRange finish_range(int blk, int irb, int Hi, in
   return r;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs a) {
+// KK / SS: compile-time kernel size and stride (3,1 | 4,2) so the tap arithmetic has no integer divisions; 0,0 = generic.
+template <typename T, int KK, int SS>
+__global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
+  FinishArgs a = aa;
+  if (KK) { a.k = KK; a.stride = SS; a.pad = 1; }
   extern __shared__ __align__(16) float fsm[];
   const int b = blockIdx.x / a.nblk, blk = blockIdx.x - b * a.nblk, tid = threadIdx.x;
   const FinishRange R = finish_range(blk, a.irb, a.Hi, a.Ho, a.k, a.stride, a.pad);
@@ -275,17 +278,22 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs a) {
     const int oyl = pix / a.Wo, ox = pix - oyl * a.Wo, oy = R.oa + oyl;
     float h[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < a.nc; ++c) h[c] = a.bias[c];
-    for (int kh = 0; kh < a.k; ++kh) {
+    const int kk = KK ? KK : a.k, ss = KK ? SS : a.stride;
+#pragma unroll
+    for (int kh = 0; kh < (KK ? KK : 4); ++kh) {
+      if (kh >= kk) break;
       const int ny = oy + a.pad - kh;
-      if (ny < 0 || ny % a.stride) continue;
-      const int iy = ny / a.stride;
+      if (ny < 0 || ny % ss) continue;
+      const int iy = ny / ss;
       if (iy >= a.Hi) continue;
-      for (int kw = 0; kw < a.k; ++kw) {
+#pragma unroll
+      for (int kw = 0; kw < (KK ? KK : 4); ++kw) {
+        if (kw >= kk) break;
         const int nx = ox + a.pad - kw;
-        if (nx < 0 || nx % a.stride) continue;
-        const int ix = nx / a.stride;
+        if (nx < 0 || nx % ss) continue;
+        const int ix = nx / ss;
         if (ix >= a.Wi) continue;
-        const float* yr = Ys + (size_t)((iy - R.ia) * a.Wi + ix) * pitch + (kh * a.k + kw) * a.nc;
+        const float* yr = Ys + (size_t)((iy - R.ia) * a.Wi + ix) * pitch + (kh * kk + kw) * a.nc;
         for (int c = 0; c < a.nc; ++c) h[c] += yr[c];
       }
     }
@@ -327,9 +335,10 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs a) {
     for (int s2 = 0; s2 < EPC / 4; ++s2) {
       const int slot = j * (EPC / 4) + s2;
       float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (slot < a.k * a.k) {
-        const int kh = slot / a.k, kw = slot - kh * a.k;
-        const int oy = iy * a.stride - a.pad + kh, ox = ix * a.stride - a.pad + kw;
+      const int kk2 = KK ? KK : a.k, ss2 = KK ? SS : a.stride;
+      if (slot < kk2 * kk2) {
+        const int kh = slot / kk2, kw = slot - kh * kk2;
+        const int oy = iy * ss2 - a.pad + kh, ox = ix * ss2 - a.pad + kw;
         if (oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo)
           gv = *reinterpret_cast<const float4*>(gS + (size_t)((oy - R.oa) * a.Wo + ox) * 4);
       }
@@ -375,15 +384,21 @@ int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, 
   a.irb = finish_irb(y);
   a.nblk = ceil_div(y.Hin, a.irb);
   const size_t smem = finish_smem_for(y, a.irb);
+  auto go = [&](auto kern) -> int {
+    DAMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * a.nblk, 256, smem, stream>>>(a);
+    DAMC_CUDA(cudaGetLastError());
+    return DAMC_OK;
+  };
+  const bool same = y.k == 3 && y.stride == 1 && y.pad == 1, up = y.k == 4 && y.stride == 2 && y.pad == 1;
   if (precision == DAMC_PREC_BF16) {
-    DAMC_CUDA(cudaFuncSetAttribute(last_finish_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    last_finish_kernel<__nv_bfloat16><<<B * a.nblk, 256, smem, stream>>>(a);
-  } else {
-    DAMC_CUDA(cudaFuncSetAttribute(last_finish_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    last_finish_kernel<float><<<B * a.nblk, 256, smem, stream>>>(a);
+    if (same) return go(last_finish_kernel<__nv_bfloat16, 3, 1>);
+    if (up) return go(last_finish_kernel<__nv_bfloat16, 4, 2>);
+    return go(last_finish_kernel<__nv_bfloat16, 0, 0>);
   }
-  DAMC_CUDA(cudaGetLastError());
-  return DAMC_OK;
+  if (same) return go(last_finish_kernel<float, 3, 1>);
+  if (up) return go(last_finish_kernel<float, 4, 2>);
+  return go(last_finish_kernel<float, 0, 0>);
 }
 
 template <typename T>

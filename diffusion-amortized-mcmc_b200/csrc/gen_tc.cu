@@ -285,7 +285,7 @@ struct StagedEpi {
   __device__ __forceinline__ static unsigned long long act_ptr_bits(const GemmPlan& p, const RowCtx& rc) {
     return (unsigned long long)(reinterpret_cast<const __nv_bfloat16*>(p.epi.act) + (rc.ok ? (long long)rc.m * p.N : 0ll));
   }
-  __device__ __forceinline__ void set_out(const GemmPlan& p, const RowCtx& rc) {
+  __device__ __forceinline__ void set_out(const GemmPlan& p, const RowCtx& rc, int cls) {
     const Epilogue& e = p.epi;
     __nv_bfloat16* out_row = nullptr;
     if (rc.ok) {
@@ -300,8 +300,9 @@ struct StagedEpi {
         }
         out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
       } else {
+        const int py = p.ncls > 1 ? (cls >> 1) : e.py, px = p.ncls > 1 ? (cls & 1) : e.px;
         out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)rc.b * e.o_b +
-                  (long long)(rc.y * e.sy + e.py) * e.o_y + (long long)(rc.x * e.sx + e.px) * e.o_x;
+                  (long long)(rc.y * e.sy + py) * e.o_y + (long long)(rc.x * e.sx + px) * e.o_x;
       }
     }
     out_bits = (unsigned long long)out_row;
@@ -379,6 +380,17 @@ struct StagedEpi {
   }
 };
 
+// taps of output-parity class cls = py*2+px of a k4-s2-p1 transposed convolution (see gen_driver.cu: up_fwd_taps)
+__device__ __forceinline__ Tap up_fwd_tap(int cls, int t) {
+  const int py = cls >> 1, px = cls & 1, ty = t >> 1, tx = t & 1;
+  Tap r;
+  r.plane = 0;
+  r.dy = (signed char)(py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0));
+  r.dx = (signed char)(px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0));
+  r.pad = 0;
+  return r;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------------
 // EW = epilogue warps: 8 for MMA-bound launches; 16 (four per TMEM lane quarter) when K is so short that the epilogue
 // is the critical path and needs the extra issue slots.
@@ -423,8 +435,10 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const GemmPlan& p = P.plan;
   const int m_units = (P.m_tiles + CG - 1) / CG;
-  const int total_tiles = m_units * P.n_tiles * p.ksplit;
+  const int ncls = p.ncls > 1 ? p.ncls : 1;
+  const int total_tiles = m_units * P.n_tiles * p.ksplit * ncls;
 
+  // tile -> (m tile, n tile, K split | parity class).  sp carries the split index, or the class when ncls > 1.
   auto decode = [&](int tile, int& mt, int& nt, int& sp) {
     nt = tile % P.n_tiles;
     const int r = tile / P.n_tiles;
@@ -445,10 +459,12 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int mt, nt, sp, b0, y0;
         decode(tile, mt, nt, sp);
         tile_origin(mt, b0, y0);
-        const int kb0 = sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        const int cls = ncls > 1 ? sp : 0;
+        const int kb0 = ncls > 1 ? 0 : sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        const int wrow0 = cls * p.ntaps * p.Np;  // class block inside the weight tensor
         for (int kb = kb0; kb < kb1; ++kb) {
           const int t = kb / P.kb_per_tap, c0 = (kb - t * P.kb_per_tap) * TC_BK;
-          const Tap tp = p.taps[t];
+          const Tap tp = ncls > 1 ? up_fwd_tap(cls, t) : p.taps[t];
           mbar_wait(bar_empty(stage), phase ^ 1u);
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           if (CG == 2) {
@@ -456,11 +472,11 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (cta_rank == 0) mbar_expect_tx(bar_full(stage), 2u * (P.a_box_bytes + P.b_box_bytes));
             const uint32_t lead_full = mapa_u32(bar_full(stage), 0u);
             tma_load_5d_2sm(sa, &tmA, lead_full, c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
-            tma_load_2d_2sm(sa + TC_A_BYTES, &tmB, lead_full, c0, t * p.Np + nt * P.BN + (int)cta_rank * (P.BN / 2));
+            tma_load_2d_2sm(sa + TC_A_BYTES, &tmB, lead_full, c0, wrow0 + t * p.Np + nt * P.BN + (int)cta_rank * (P.BN / 2));
           } else {
             mbar_expect_tx(bar_full(stage), P.a_box_bytes + P.b_box_bytes);
             tma_load_5d(sa, &tmA, bar_full(stage), c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
-            tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, t * p.Np + nt * P.BN);
+            tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, wrow0 + t * p.Np + nt * P.BN);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
@@ -475,7 +491,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
         int mt, nt, sp;
         decode(tile, mt, nt, sp);
-        const int kb0 = sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        const int kb0 = ncls > 1 ? 0 : sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(bar_tempty(as), aphase ^ 1u);  // epilogue has drained this accumulator
@@ -563,7 +579,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int as = k & 1;
           if (sg == 0) {
             const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
-            se.set_out(p, rc);
+            se.set_out(p, rc, sp);
           }
           const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
           if (is_mask) {
@@ -656,6 +672,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   if (p.Cs % TC_BK) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, TC_BK);
   if (p.Np % 16) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: padded N (%d) must be a multiple of 16", p.Np);
   if (p.Wm > TC_BM) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: pixel-grid width %d > %d", p.Wm, TC_BM);
+  if (p.ncls > 1 && (p.ncls != 4 || p.ntaps != 4 || p.ksplit != 1 || p.epi.kind != EPI_FWD_ACT || p.Np % 64))
+    DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: merged parity classes need the k4-s2-p1 forward shape");
   TcParams P{};
   P.plan = p;
   P.BN = p.Np < 256 ? p.Np : 256;
@@ -711,7 +729,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (Cs=%d W=%d H=%d B=%d planes=%d)", (int)r, p.Cs, p.Wm, p.Hm, p.B, nplanes);
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)p.ntaps * p.Np};
+    const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)(p.ncls > 1 ? p.ncls : 1) * p.ntaps * p.Np};
     const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(P.BN / cg)};
     const cuuint32_t estr[2] = {1, 1};
@@ -735,7 +753,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   if (cg == 2) {
-    const int units = ceil_div(P.m_tiles, 2) * P.n_tiles * p.ksplit;
+    const int units = ceil_div(P.m_tiles, 2) * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * std::min(units, num_sms / 2));
     cfg.blockDim = dim3(64 + 32 * 8);
@@ -748,7 +766,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, tmA, tmB, P));
     return DAMC_OK;
   }
-  const int total = P.m_tiles * P.n_tiles * p.ksplit;
+  const int total = P.m_tiles * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
   if (ew == 16) convgemm_tc_kernel<16, 1><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(tmA, tmB, P);
   else convgemm_tc_kernel<8, 1><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(tmA, tmB, P);
   DAMC_CUDA(cudaGetLastError());
