@@ -33,6 +33,7 @@ struct TcParams {
   int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
   int Ht, Bt, tiles_per_img, tile_rows;
   uint32_t a_box_bytes, b_box_bytes, idesc;
+  int cls_inner;    // merged parity classes: class index is the fastest tile dimension
   int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
 };
 
@@ -440,6 +441,13 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   // tile -> (m tile, n tile, K split | parity class).  sp carries the split index, or the class when ncls > 1.
   auto decode = [&](int tile, int& mt, int& nt, int& sp) {
+    if (ncls > 1 && P.cls_inner) {  // classes innermost: the 4 classes of one input window run back to back and share it through L2
+      sp = tile % ncls;
+      tile /= ncls;
+      nt = tile % P.n_tiles;
+      mt = (tile / P.n_tiles) * CG + (int)cta_rank;
+      return;
+    }
     nt = tile % P.n_tiles;
     const int r = tile / P.n_tiles;
     mt = (r % m_units) * CG + (int)cta_rank;   // this CTA's 128-row tile (may lie past the end: rows are masked)
@@ -698,6 +706,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   P.a_box_bytes = (uint32_t)P.tile_rows * TC_BK * 2;
   P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
   P.stage_cols = 0;
+  P.cls_inner = getenv("DAMC_TC_CLS_OUTER") ? 0 : 1;
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
     if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
   }
