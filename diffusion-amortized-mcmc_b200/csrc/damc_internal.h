@@ -52,6 +52,9 @@ struct Epilogue {
   // EPI_DGRAD_MASK: sign source = activation of the producing layer, NHWC on the M grid, C = N
   const void* act;
   int planar_out;       // 1: scatter (y,x) into 4 parity planes [4][B][Hm/2][Wm/2][N]; 0: flat [M][N]
+  // tcgen05 engine only: 1 bit per activation element ("pre-activation > 0"), word index = NHWC element index / 32.
+  // Written by EPI_FWD_ACT, read by EPI_DGRAD_MASK instead of the 16x larger activation rows.  null = use `act`.
+  uint32_t* maskbits;
   // EPI_FWD_LAST
   const float* x;       // [B,nc,Ho,Wo] or null (forward only)
   float* xhat;          // [B,nc,Ho,Wo] or null
@@ -104,6 +107,7 @@ struct GenPack : damc_handle {
   std::vector<void*> allocs;
   int dz_splits = 1;
   bool last_scatter = false;  // last layer runs as scatter-form GEMM + per-image finish kernel (image fits in smem)
+  bool use_bits = false;    // tcgen05 engine: LeakyReLU masks travel as 1-bit-per-element words
   bool use_tc = false;      // bf16 mode: tcgen05 engine (default) or the SIMT engine on bf16 storage (DAMC_TC=0)
   ~GenPack() override { for (void* p : allocs) cudaFree(p); }
   int refill(cudaStream_t stream) override;
@@ -113,6 +117,7 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
   void* zin;                 // [B][nz_p]          T
   std::vector<void*> act;    // a_1..a_{L-1}       T (NHWC)
   std::vector<void*> grad;   // g_1..g_{L-1}       T (planar for L_UP producers, flat for L_FIRST)
+  std::vector<uint32_t*> mask;  // sign bits of a_1..a_{L-1} (tcgen05 engine) or null
   void* gcol;                // [B*Hi*Wi][64]      T
   float* ybuf;               // [B*Hi*Wi][np_sc]   fp32 (scatter-form last layer) or null
   float* dz_part;            // [splits][B][nz_p]  fp32

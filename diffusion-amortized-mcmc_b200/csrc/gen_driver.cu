@@ -70,6 +70,7 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
   g->src.assign(L, L + nlayers);
   const char* env = getenv("DAMC_TC");
   g->use_tc = precision == DAMC_PREC_BF16 && !(env && env[0] == '0');
+  g->use_bits = g->use_tc && !getenv("DAMC_TC_NOBITS");
   if (g->use_tc && !tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "bf16 mode needs cuTensorMapEncodeTiled from the driver (no fallback)");
   return g->refill(stream);
 }
@@ -145,11 +146,13 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   ws->zin = take(es * (size_t)B * g->nz_p);
   ws->act.assign(L - 1, nullptr);
   ws->grad.assign(L - 1, nullptr);
+  ws->mask.assign(L - 1, nullptr);
   for (int l = 0; l < L - 1; ++l) {
     const GenLayer& y = g->layers[l];
     const size_t n = (size_t)B * y.Hout * y.Wout * y.cout;
     ws->act[l] = take(es * n);
     ws->grad[l] = take(es * n);
+    if (g->use_bits) ws->mask[l] = (uint32_t*)take(n / 8);
   }
   const GenLayer& last = g->layers[L - 1];
   ws->gcol = take(es * (size_t)B * last.Hin * last.Win * 64);
@@ -216,6 +219,7 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     } else {
       e.kind = EPI_FWD_ACT;
       e.out = ws.act[l];
+      e.maskbits = ws.mask[l];
       e.bias_mod = y.cout;
       if (y.type == L_FIRST) { e.o_b = (long long)y.n_fwd; e.o_y = 0; e.o_x = 0; }
       else { e.o_b = (long long)y.Hout * y.Wout * y.cout; e.o_y = (long long)y.Wout * y.cout; e.o_x = y.cout; }
@@ -279,6 +283,7 @@ int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_
       p.ksplit = dz_splits_for(g, B);
     } else {
       e.kind = EPI_DGRAD_MASK;
+      e.maskbits = ws.mask[l - 1];
       e.act = ws.act[l - 1];
       e.out = ws.grad[l - 1];
       e.planar_out = g->layers[l - 1].type == L_UP;

@@ -281,6 +281,7 @@ struct StagedEpi {
   static constexpr int CPR = 8, SW = 64, RPI = 4, NIT = 8;
   static constexpr uint32_t row_bytes = SW * 2;
   unsigned long long out_bits;
+  unsigned long long mrow_bits;  // this lane's row of mask words (1 bit per element), or 0
   int sub, j;
 
   __device__ __forceinline__ static unsigned long long act_ptr_bits(const GemmPlan& p, const RowCtx& rc) {
@@ -307,6 +308,17 @@ struct StagedEpi {
       }
     }
     out_bits = (unsigned long long)out_row;
+    mrow_bits = 0ull;
+    if (e.maskbits != nullptr && rc.ok) {
+      const long long elem0 = e.kind == EPI_DGRAD_MASK ? (long long)rc.m * p.N
+                                                       : (long long)(out_row - reinterpret_cast<__nv_bfloat16*>(e.out));
+      mrow_bits = (unsigned long long)(e.maskbits + (elem0 >> 5));
+    }
+  }
+  // mask words of the 64-column segment at n_base for this lane's row (dgrad; rows outside the problem read word 0)
+  __device__ __forceinline__ static uint2 load_mask_words(const GemmPlan& p, const RowCtx& rc, int n_base) {
+    const uint32_t* w = p.epi.maskbits + (rc.ok ? (((long long)rc.m * p.N + n_base) >> 5) : 0ll);
+    return __ldg(reinterpret_cast<const uint2*>(w));
   }
   // issue the 8 coalesced 16-byte loads of one 32-row x 64-column activation segment
   __device__ __forceinline__ void request(uint4 (&r)[NIT], unsigned long long act_bits, int n_base) const {
@@ -328,20 +340,33 @@ struct StagedEpi {
     __syncwarp();
   }
   // accumulators of one segment -> epilogue math -> smem -> global
-  __device__ __forceinline__ void process(const GemmPlan& p, uint32_t t_seg, uint32_t my_stage, int lane, int n_base) const {
+  __device__ __forceinline__ void process(const GemmPlan& p, uint32_t t_seg, uint32_t my_stage, int lane, int n_base,
+                                          uint2 mw) const {
     const Epilogue& e = p.epi;
     const bool is_mask = e.kind == EPI_DGRAD_MASK;
+    const bool bits = e.maskbits != nullptr;
+    uint32_t wout[2] = {0u, 0u};
 #pragma unroll 1
     for (int c = 0; c < SW; c += 32) {
       uint32_t v[32];
       tmem_ld32(t_seg + (uint32_t)c, v);
       tmem_ld_wait();
+      const uint32_t mword = c == 0 ? mw.x : mw.y;
+      uint32_t oword = 0u;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int jj = (c >> 3) + g;
         const uint32_t addr = my_stage + (uint32_t)lane * row_bytes + (uint32_t)((jj ^ (lane & (CPR - 1))) << 4);
         uint32_t w[4];
-        if (is_mask) {
+        if (is_mask && bits) {
+#pragma unroll
+          for (int t2 = 0; t2 < 4; ++t2) {
+            float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
+            if (!((mword >> (8 * g + 2 * t2)) & 1u)) g0 *= e.slope;
+            if (!((mword >> (8 * g + 2 * t2 + 1)) & 1u)) g1 *= e.slope;
+            w[t2] = pack_bf16x2(g0, g1);
+          }
+        } else if (is_mask) {
           uint32_t aw[4];
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(aw[0]), "=r"(aw[1]), "=r"(aw[2]), "=r"(aw[3]) : "r"(addr) : "memory");
 #pragma unroll
@@ -359,14 +384,17 @@ struct StagedEpi {
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
             float h0 = __uint_as_float(v[8 * g + 2 * t2]) + bb[2 * t2], h1 = __uint_as_float(v[8 * g + 2 * t2 + 1]) + bb[2 * t2 + 1];
-            h0 = h0 > 0.f ? h0 : e.slope * h0;
-            h1 = h1 > 0.f ? h1 : e.slope * h1;
+            if (h0 > 0.f) oword |= 1u << (8 * g + 2 * t2); else h0 *= e.slope;
+            if (h1 > 0.f) oword |= 1u << (8 * g + 2 * t2 + 1); else h1 *= e.slope;
             w[t2] = pack_bf16x2(h0, h1);
           }
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
       }
+      wout[c >> 5] = oword;
     }
+    if (!is_mask && bits && mrow_bits)  // sign bits of this row's 64 pre-activations (consumed by the dgrad epilogue)
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(mrow_bits) + (n_base >> 5)) = make_uint2(wout[0], wout[1]);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {  // write-out: 8 consecutive lanes cover one contiguous 128-byte row piece
@@ -549,6 +577,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (P.stage_cols == 64) {
       // ---- staged path: flat software pipeline over (tile, segment) items of this warp ----
       const bool is_mask = p.epi.kind == EPI_DGRAD_MASK;
+      const bool bits = p.epi.maskbits != nullptr;  // dgrad reads 8 bytes of sign bits per row segment, not 128
       const int nseg_w = (P.BN / 64 - grp + NG - 1) / NG;  // segments of a tile handled by this warp: grp, grp+NG, ...
       const int ntl = (total_tiles - unit + nunits - 1) / nunits;
       const uint32_t tempty_lead[2] = {CG == 2 ? mapa_u32(bar_tempty(0), 0u) : 0u, CG == 2 ? mapa_u32(bar_tempty(1), 0u) : 0u};
@@ -574,7 +603,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           int nt, sp;
           const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
           const int n_base = nt * P.BN + (grp + NG * sg) * 64;
-          if (n_base < p.N) se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
+          if (n_base >= p.N) return;
+          if (bits) { const uint2 mw = StagedEpi::load_mask_words(p, rc, n_base); r[0].x = mw.x; r[0].y = mw.y; }
+          else se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
         };
         constexpr int AHEAD = EW == 8 ? 2 : 1;  // 16 warps: one register set each (keeps the kernel spill-free)
         request(ra, 0);
@@ -590,15 +621,16 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             se.set_out(p, rc, sp);
           }
           const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
+          uint2 mw = make_uint2(0u, 0u);
           if (is_mask) {
-            se.stash(r, my_stage);
+            if (bits) mw = make_uint2(r[0].x, r[0].y); else se.stash(r, my_stage);
             request(r, item + AHEAD);
           }
           if (sg == 0) {
             mbar_wait(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
             tc_fence_after();
           }
-          if (n_base < p.N) se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base);
+          if (n_base < p.N) se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base, mw);
           if (sg == nseg_w - 1) {
             tc_fence_before();
             __syncwarp();
@@ -710,6 +742,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
     if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
   }
+  if (!P.stage_cols && p.epi.maskbits != nullptr && (p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK))
+    DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: bit masks need the staged epilogue (N %% 64 == 0); set DAMC_TC_NOBITS=1");
   const int ew = (P.stage_cols && P.kb_per_split <= 4 && P.BN >= 256 && !getenv("DAMC_TC_EW8")) ? 16 : 8;
   // CTA-pair MMA for the MMA-bound launches: full 256-wide N tiles, long K, an even grid of pairs
   static const bool allow_2sm = []{ const char* e = getenv("DAMC_TC_2SM"); return !(e && e[0] == '0'); }();

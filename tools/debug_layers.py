@@ -72,6 +72,8 @@ def main():
         off += al(es * n)
         graw = ws[off:off + es * n].view(tdt).float()
         off += al(es * n)
+        if prec == "bf16" and not os.environ.get("DAMC_TC_NOBITS") and os.environ.get("DAMC_TC", "1") != "0":
+            off += al(n // 8)  # 1-bit LeakyReLU masks of this layer (tcgen05 engine)
         if l == 0:
             gg = graw.reshape(B, H, H, cout).permute(0, 3, 1, 2).cpu()
         else:  # planar [py][px][B][H/2][W/2][C]
