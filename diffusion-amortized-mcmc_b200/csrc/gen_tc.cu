@@ -33,6 +33,7 @@ struct TcParams {
   int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
   int Ht, Bt, tiles_per_img, tile_rows;
   uint32_t a_box_bytes, b_box_bytes, idesc;
+  int wm_shift, per_img_shift;  // log2(Wm), log2(Ht*Wm) when powers of two, else -1 (row decode without divisions)
   int cls_inner;    // merged parity classes: class index is the fastest tile dimension
   int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
 };
@@ -565,10 +566,14 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int r = q * 32 + lane;
       RowCtx rc;
       const int per_img = P.Ht * p.Wm;
-      const int bt = r / per_img, rem = r - bt * per_img;
+      int bt, rem, yy, xx;
+      if (P.per_img_shift >= 0) { bt = r >> P.per_img_shift; rem = r & (per_img - 1); }
+      else { bt = r / per_img; rem = r - bt * per_img; }
+      if (P.wm_shift >= 0) { yy = rem >> P.wm_shift; xx = rem & (p.Wm - 1); }
+      else { yy = rem / p.Wm; xx = rem - yy * p.Wm; }
       rc.b = b0 + bt;
-      rc.y = y0 + rem / p.Wm;
-      rc.x = rem % p.Wm;
+      rc.y = y0 + yy;
+      rc.x = xx;
       rc.ok = r < P.tile_rows && rc.b < p.B && rc.y < p.Hm;
       rc.m = (rc.b * p.Hm + rc.y) * p.Wm + rc.x;
       return rc;
@@ -730,6 +735,9 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     P.m_tiles = ceil_div(p.B, P.Bt);
   }
   P.tile_rows = p.Wm * P.Ht * P.Bt;
+  auto log2_or_neg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+  P.wm_shift = log2_or_neg(p.Wm);
+  P.per_img_shift = log2_or_neg(P.Ht * p.Wm);
   P.kb_per_tap = p.Cs / TC_BK;
   P.kb_total = p.ntaps * P.kb_per_tap;
   P.kb_per_split = ceil_div(P.kb_total, p.ksplit);
