@@ -310,6 +310,21 @@ def gen_samples_with_diffusion_prior(b, device, netQ, netG, *, precision=None):
     return x, zk_prior
 
 
+def recon_mse(x, z, netG, *, precision=None):
+    """sum_b mean_pixels (G(z_b) - x_b)^2 -- the quantity accumulated at eval_gen_recon.py:192-194 /
+    train_gen_recon.py:340-343 after the noise-free Langevin refinement."""
+    x_hat = generator_forward(netG, z, precision)
+    return torch.mean((x_hat - x) ** 2, dim=[1, 2, 3]).sum()
+
+
+def anomaly_score(x, z, netG, netE, *, precision=None):
+    """Per-sample score |G(z)-x|^2 + E(z) + |z|^2/2 of eval_anomaly_det.py:114-119 (G through the packed kernels)."""
+    x_hat = generator_forward(netG, z, precision)
+    with torch.no_grad():
+        s_hat = netE(z)
+    return torch.sum((x_hat - x) ** 2, dim=[1, 2, 3]) + s_hat + 0.5 * torch.sum(z ** 2, dim=-1)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # DAMC ancestral sampler
 # ----------------------------------------------------------------------------------------------------------------------

@@ -210,3 +210,31 @@ class _netQ_U(nn.Module):
     def forward(self, x=None, b=None, device=None, cond_w=-1, noise=None):
         from . import MCMC  # late import: MCMC needs the CUDA library
         return MCMC.damc_sample(self, x=x, b=b, device=device, cond_w=cond_w, noise=noise)
+
+    def calculate_loss(self, x=None, z=None, mask=None):
+        """Denoising loss 0.5*|eps - eps_hat|^2 per sample at a random noise level (reference diffusion_net.py:624-646).
+        Training-side code: ordinary PyTorch autograd (outside the CUDA hot path)."""
+        assert z is not None
+        n = len(z)
+        if x is not None:
+            xemb = self.encoder(x)
+            if mask is not None:
+                xemb = xemb * mask + self.prior_emb(torch.randn(len(x), self.nz, device=x.device)) * (1 - mask)
+        else:
+            assert mask is None
+            xemb = self.prior_emb(torch.randn(n, self.nz, device=z.device))
+        u = torch.rand(n).to(z.device)
+        logsnr = logsnr_schedule_fn(u, logsnr_min=self.logsnr_min, logsnr_max=self.logsnr_max)
+        lam = logsnr.reshape(n, 1)
+        eps = torch.randn_like(z)
+        zt = z * torch.sqrt(torch.sigmoid(lam)) + torch.sqrt(torch.sigmoid(-lam)) * eps
+        eps_pred = self.p(z=zt, logsnr=logsnr, xemb=xemb)
+        return 0.5 * torch.sum((eps - eps_pred) ** 2, dim=1)
+
+
+def logsnr_schedule_fn(t, logsnr_min=-20.0, logsnr_max=20.0):
+    """lambda(t) = -2 log tan(a t + b), b = atan(exp(-lambda_max/2)), a = atan(exp(-lambda_min/2)) - b
+    (reference diffusion_helper_func.py:41-50)."""
+    b = torch.arctan(torch.exp(-0.5 * torch.full_like(t, logsnr_max)))
+    a = torch.arctan(torch.exp(-0.5 * torch.full_like(t, logsnr_min))) - b
+    return -2.0 * torch.log(torch.tan(a * t + b))

@@ -109,3 +109,28 @@ def test_toy_oracle_matches_reference():
                for i, d in enumerate(dims)]
         z = O.toy_langevin_posterior(z0.to(dt), x.to(dt), mlp, K, True, float(g["step"]), noise.to(dt))
         assert relmax(z, g["z_" + tag]) < tol, tag
+
+
+def test_calculate_loss_mirror_matches_reference():
+    """Training-side mirror (_netQ_U.calculate_loss) against the reference with injected randn / rand draws."""
+    from damc_b200 import diffusion_net as dn
+    g = np.load(os.path.join(GOLDEN, "qloss_cifar10.npz"))
+    B, nz, nxemb, T = (int(v) for v in g["cfg"])
+    Q = dn._netQ_U(nc=3, nz=nz, nxemb=nxemb, ntemb=128, nif=64, diffusion_residual=True, n_interval=T,
+                   logsnr_min=-5.1, logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10")
+    Q.load_state_dict(synth.module_state_like(Q, prefix="Q."))
+    Q.eval()
+    x = torch.tanh(synth.det_normal("x", (B, 3, 32, 32)))
+    z, mask = synth.det_normal("lz", (B, nz)), (synth.det_normal("lmask", (B, 1)) > 0).float()
+    draws = iter([synth.det_normal("prior_z", (B, nz)), synth.det_normal("leps", (B, nz))])
+    u = torch.sigmoid(synth.det_normal("lu", (B,)))
+    real = (torch.randn, torch.randn_like, torch.rand)
+    torch.randn = lambda *a, **k: next(draws).clone()
+    torch.randn_like = lambda t, **k: next(draws).clone()
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        with torch.no_grad():
+            loss = Q.calculate_loss(x=x, z=z, mask=mask)
+    finally:
+        torch.randn, torch.randn_like, torch.rand = real
+    assert relmax(loss, g["loss"]) < 1e-5
