@@ -213,7 +213,8 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
     DAMC_TRY(generator_forward(g, ws, z, B, x, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, s));
     DAMC_TRY(generator_dgrad(g, ws, B, s));
     DAMC_TRY(launch_ebm_step(m, z, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
-                             chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p, g->nz, s));
+                             chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
+                             1.0f / generator_grad_scale(g, sigma), g->nz, s));
   }
   return DAMC_OK;
 }

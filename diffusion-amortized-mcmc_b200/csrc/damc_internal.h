@@ -30,7 +30,7 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
 // single Langevin step for many chains with the MLP streamed from L2 (the posterior sampler's per-step tail)
 int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
                     uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
-                    int nz_if_no_ebm, cudaStream_t stream);
+                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream);
 int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
 
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
@@ -59,6 +59,7 @@ struct Epilogue {
   const float* x;       // [B,nc,Ho,Wo] or null (forward only)
   float* xhat;          // [B,nc,Ho,Wo] or null
   float inv_sigma2;
+  float gscale;         // factor carried by the stored gradient chain (sigma^2 in fp16 mode, else 1); undone in the update
   float* loss;          // null or scalar accumulator: sum (xhat-x)^2 * inv_sigma2/2
   void* gcol;           // im2col'd dL/dh_last for the last layer's dgrad: [B*Hi*Wi][64], slot (kh*k+kw)*4 + c
   int nc, k, stride, padding, Hi, Wi, Ho, Wo;
@@ -76,6 +77,7 @@ struct GemmPlan {
   const void* Wtc;          // tcgen05 engine: [ntaps][Np][Cs] bf16 (K contiguous), or null
   int N, Np;                // logical / padded (multiple of 16) output columns
   int ksplit;               // >1: grid.z splits the K loop (EPI_DGRAD_Z only)
+  int op_fp16;              // tcgen05 engine: operands / stored tensors are fp16 (else bf16); set by launch_gemm_tc
   int ncls;                 // tcgen05 engine only: 4 = all output-parity classes of a k4-s2-p1 forward in ONE launch
                             // (taps and epilogue parity derived from the class; Wtc holds the 4 class blocks back to back)
   Epilogue epi;
@@ -125,12 +127,13 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
 };
 
 size_t elem_size(int precision);
+static inline bool is_tc_precision(int precision) { return precision == DAMC_PREC_BF16 || precision == DAMC_PREC_FP16; }
 int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws);
 
 // SIMT implicit GEMM (fp32 or bf16 storage, fp32 accumulate) -- gen_simt.cu
 int launch_gemm_simt(const GemmPlan& p, int precision, cudaStream_t stream);
 // tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate) -- gen_tc.cu
-int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream);
+int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream);
 int tc_available();
 
 // weight packing -- gen_pack.cu
@@ -139,12 +142,13 @@ int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int 
                       int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream);
 size_t last_finish_smem(const GenLayer& y);
 int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
-                       float inv_sigma2, float* loss, void* gcol, cudaStream_t stream);
+                       float inv_sigma2, float gscale, float* loss, void* gcol, cudaStream_t stream);
 int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int precision, cudaStream_t stream);
 
 // generator driver -- gen_driver.cu
 int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
                       float* xhat, float* loss, cudaStream_t stream);
+float generator_grad_scale(const GenPack* g, float sigma);
 int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream);
 
 }  // namespace damc

@@ -384,19 +384,21 @@ struct EbmStepArgs {
   float* trace;        // null or [4]: sum E, (llhd), |z|^2/2, mean grad
   const float* gpart;
   int nsplit, gstride;
+  float gpart_scale;   // multiplies the summed generator partials (undoes the fp16 mode's sigma^2 scaling)
   float inv_count;
 };
 
-// acc[c] += sum_i W[i*ld + col] * vec[i*CH + c], with the weight loads issued 8 at a time (L2 latency overlap)
-template <int CH>
-__device__ __forceinline__ void stream_matvec(const float* __restrict__ Wcol, int ld, int n, const float* vec, float (&acc)[CH]) {
-  int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    float w[8];
+// acc[c] += sum_i W[i*ld + col] * vec[i*CH + c].  The weight column is fetched in batches of U independent loads (32,
+// then 8, then 1): with ~1 us of L2/HBM latency per round trip the number of round trips, not the FMA count, is the cost.
+template <int CH, int U>
+__device__ __forceinline__ int stream_matvec_batch(const float* __restrict__ Wcol, int ld, int i, int n, const float* vec,
+                                                   float (&acc)[CH]) {
+  for (; i + U <= n; i += U) {
+    float w[U];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) w[u] = __ldg(Wcol + (size_t)(i + u) * ld);
+    for (int u = 0; u < U; ++u) w[u] = __ldg(Wcol + (size_t)(i + u) * ld);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int c4 = 0; c4 < CH / 4; ++c4) {
         const float4 v = *reinterpret_cast<const float4*>(vec + (i + u) * CH + 4 * c4);
@@ -405,11 +407,13 @@ __device__ __forceinline__ void stream_matvec(const float* __restrict__ Wcol, in
       }
     }
   }
-  for (; i < n; ++i) {
-    const float w = __ldg(Wcol + (size_t)i * ld);
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[c] = fmaf(w, vec[i * CH + c], acc[c]);
-  }
+  return i;
+}
+template <int CH>
+__device__ __forceinline__ void stream_matvec(const float* __restrict__ Wcol, int ld, int n, const float* vec, float (&acc)[CH]) {
+  int i = stream_matvec_batch<CH, 32>(Wcol, ld, 0, n, vec, acc);
+  i = stream_matvec_batch<CH, 8>(Wcol, ld, i, n, vec, acc);
+  stream_matvec_batch<CH, 1>(Wcol, ld, i, n, vec, acc);
 }
 
 template <int CH>
@@ -486,8 +490,11 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
     for (int c = 0; c < nvalid; ++c) {
       const size_t chain = (size_t)(c0 + c);
       float g = gE[c];
-      if (a.gpart != nullptr)
-        for (int s = 0; s < a.nsplit; ++s) g += a.gpart[((size_t)s * a.B + chain) * a.gstride + tid];
+      if (a.gpart != nullptr) {
+        float gg = 0.f;
+        for (int s = 0; s < a.nsplit; ++s) gg += a.gpart[((size_t)s * a.B + chain) * a.gstride + tid];
+        g = fmaf(gg, a.gpart_scale, g);
+      }
       const float zv = zs[tid * CH + c];
       const float grad = g + zv;
       float nrm = 0.f;
@@ -513,8 +520,8 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
 
 int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
                     uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
-                    int nz_if_no_ebm, cudaStream_t stream) {
-  constexpr int CH = 8;
+                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream) {
+  constexpr int CH = 4;  // small chain tiles: two or more CTAs per SM overlap each other's L2 latency
   EbmStepArgs a{};
   a.use_ebm = m != nullptr;
   if (m) {
@@ -526,6 +533,7 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
   if (a.nz < 1 || a.nz > 256 || a.ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM step kernel: nz <= 256 and ndf <= 256 (nz=%d ndf=%d)", a.nz, a.ndf);
   a.z = z; a.B = B; a.step = step; a.with_noise = with_noise; a.noise = noise; a.seed = seed; a.chain0 = chain0;
   a.step_index = step_index; a.trace = trace4; a.gpart = gpart; a.nsplit = nsplit; a.gstride = gstride;
+  a.gpart_scale = gpart_scale;
   a.inv_count = 1.0f / ((float)B * (float)a.nz);
   const size_t smem = sizeof(float) * CH * ((size_t)a.nz + 3 * (size_t)a.ndf);
   ebm_step_kernel<CH><<<ceil_div(B, CH), 256, smem, stream>>>(a);

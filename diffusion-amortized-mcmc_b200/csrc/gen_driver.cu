@@ -31,14 +31,14 @@ static int dev_alloc(GenPack* g, void** p, size_t bytes) {
 int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision,
                     cudaStream_t stream) {
   if (nlayers < 2 || nlayers > 8) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "generator needs 2..8 ConvTranspose2d layers (got %d)", nlayers);
-  if (precision != DAMC_PREC_FP32 && precision != DAMC_PREC_BF16) DAMC_FAIL(DAMC_ERR_INVALID, "unknown precision %d", precision);
+  if (precision != DAMC_PREC_FP32 && !is_tc_precision(precision)) DAMC_FAIL(DAMC_ERR_INVALID, "unknown precision %d", precision);
   g->kind = H_GEN;
   g->precision = precision;
   g->nlayers = nlayers;
   g->slope = slope;
   g->nz = L[0].cin;
   g->nz_p = (int)align_up(g->nz, 64);
-  const int cmult = precision == DAMC_PREC_BF16 ? 64 : 16;
+  const int cmult = is_tc_precision(precision) ? 64 : 16;
   int H = 1, W = 1;
   g->layers.resize(nlayers);
   for (int i = 0; i < nlayers; ++i) {
@@ -69,7 +69,7 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
 
   g->src.assign(L, L + nlayers);
   const char* env = getenv("DAMC_TC");
-  g->use_tc = precision == DAMC_PREC_BF16 && !(env && env[0] == '0');
+  g->use_tc = is_tc_precision(precision) && !(env && env[0] == '0');
   g->use_bits = g->use_tc && !getenv("DAMC_TC_NOBITS");
   if (g->use_tc && !tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "bf16 mode needs cuTensorMapEncodeTiled from the driver (no fallback)");
   return g->refill(stream);
@@ -164,7 +164,7 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
 
 static int run_gemm(const GenPack* g, const GemmPlan& p, cudaStream_t stream) {
   profile_mark(stream, true);
-  const int r = (g->use_tc && p.Wtc) ? launch_gemm_tc(p, stream) : launch_gemm_simt(p, g->precision, stream);
+  const int r = (g->use_tc && p.Wtc) ? launch_gemm_tc(p, g->precision, stream) : launch_gemm_simt(p, g->precision, stream);
   profile_mark(stream, false);
   count_launch();
   return r;
@@ -206,7 +206,8 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
       e.kind = EPI_STORE_F32;
       e.out = ws.ybuf; e.nz_out = y.np_sc;
       DAMC_TRY(run_gemm(g, p, stream));
-      DAMC_TRY(launch_last_finish(y, g->precision, ws.ybuf, B, x, xhat, 1.0f / (sigma * sigma), loss, ws.gcol, stream));
+      DAMC_TRY(launch_last_finish(y, g->precision, ws.ybuf, B, x, xhat, 1.0f / (sigma * sigma),
+                                  generator_grad_scale(g, sigma), loss, ws.gcol, stream));
       count_launch();
       continue;
     }
@@ -214,6 +215,7 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
       e.kind = EPI_FWD_LAST;
       e.x = x; e.xhat = xhat; e.loss = loss; e.gcol = ws.gcol;
       e.inv_sigma2 = 1.0f / (sigma * sigma);
+      e.gscale = generator_grad_scale(g, sigma);
       e.nc = y.cout; e.k = y.k; e.stride = y.stride; e.padding = y.pad;
       e.Hi = y.Hin; e.Wi = y.Win; e.Ho = y.Hout; e.Wo = y.Wout;
     } else {
@@ -292,6 +294,9 @@ int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_
   }
   return DAMC_OK;
 }
+
+// fp16 mode carries dU/dh scaled by sigma^2 (O(1) magnitudes) through the backward chain; the update kernel undoes it
+float generator_grad_scale(const GenPack* g, float sigma) { return g->precision == DAMC_PREC_FP16 ? sigma * sigma : 1.0f; }
 
 int dz_splits(const GenPack* g, int B) { return dz_splits_for(g, B); }
 

@@ -1,6 +1,8 @@
 // gen_epilogue.cuh -- element loads/stores and the per-element GEMM epilogues shared by the SIMT (gen_simt.cu) and
 // tcgen05 (gen_tc.cu) engines.  See damc_internal.h for the meaning of the epilogue kinds.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "damc_common.cuh"
 #include "damc_internal.h"
 
@@ -19,6 +21,20 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float v[8]) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+__device__ __forceinline__ void load8(const __half* p, float v[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void load4(const __half* p, float v[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+__device__ __forceinline__ void store_t(__half* p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void load4(const float* p, float v[4]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -71,7 +87,7 @@ __device__ __forceinline__ void epilogue_elem(const GemmPlan& p, int split, int 
       if (e.xhat) e.xhat[xi] = xh;
       if (e.x) {
         const float r = xh - e.x[xi];
-        const float g = r * e.inv_sigma2 * (1.f - xh * xh);
+        const float g = r * e.inv_sigma2 * e.gscale * (1.f - xh * xh);
         loss_acc += 0.5f * e.inv_sigma2 * r * r;
         T* gc = reinterpret_cast<T*>(e.gcol);
         for (int kh = 0; kh < e.k; ++kh) {

@@ -13,6 +13,7 @@
 //   1x1 -> kxk first layer: a plain GEMM in both directions; last layer (Cout = nc): forward writes dL/dh already
 //   im2col'd ("gcol", 64 columns per input pixel) so its dgrad is a plain K=64 GEMM too.
 #include <algorithm>
+#include <type_traits>
 
 #include "damc_common.cuh"
 #include "damc_internal.h"
@@ -20,7 +21,7 @@
 
 namespace damc {
 
-size_t elem_size(int precision) { return precision == DAMC_PREC_BF16 ? 2 : 4; }
+size_t elem_size(int precision) { return is_tc_precision(precision) ? 2 : 4; }
 
 // ---- the SIMT kernel ----------------------------------------------------------------------------------------------
 template <typename T, int BN>
@@ -147,6 +148,7 @@ static int launch_simt_t(const GemmPlan& p, cudaStream_t stream) {
 
 int launch_gemm_simt(const GemmPlan& p, int precision, cudaStream_t stream) {
   if (p.Cs % 16 != 0 || p.Np % 4 != 0) DAMC_FAIL(DAMC_ERR_INVALID, "SIMT GEMM needs Cs%%16==0, Np%%4==0 (Cs=%d Np=%d)", p.Cs, p.Np);
+  if (precision == DAMC_PREC_FP16) return launch_simt_t<__half>(p, stream);
   return precision == DAMC_PREC_BF16 ? launch_simt_t<__nv_bfloat16>(p, stream) : launch_simt_t<float>(p, stream);
 }
 
@@ -201,7 +203,10 @@ int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int 
   (void)stride; (void)pad;
   const long long total = (long long)ntaps * Cs * Np;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  if (precision == DAMC_PREC_BF16)
+  if (precision == DAMC_PREC_FP16)
+    pack_convt_kernel<__half><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
+                                                          reinterpret_cast<__half*>(dst));
+  else if (precision == DAMC_PREC_BF16)
     pack_convt_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
                                                                  reinterpret_cast<__nv_bfloat16*>(dst));
   else
@@ -219,7 +224,7 @@ int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int 
 struct FinishArgs {
   const float* Y; const float* bias; const float* x; float* xhat; float* loss; void* gcol;
   int Hi, Wi, Ho, Wo, k, stride, pad, nc, np, irb, nblk;
-  float inv_sigma2;
+  float inv_sigma2, gscale;
 };
 
 struct FinishRange { int iy0, iy1, oa, ob, ia, ib; };
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
       if (a.xhat && own) a.xhat[xi] = xh;
       if (a.x) {
         const float r = xh - a.x[xi];
-        g[c] = r * a.inv_sigma2 * (1.f - xh * xh);
+        g[c] = r * (a.inv_sigma2 * a.gscale) * (1.f - xh * xh);
         if (own) loss_acc += 0.5f * a.inv_sigma2 * r * r;
       }
     }
@@ -351,8 +356,13 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
       uint32_t w[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(vals[2 * q], vals[2 * q + 1]);
-        w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        if constexpr (sizeof(T) == 2 && !std::is_same<T, __half>::value) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(vals[2 * q], vals[2 * q + 1]);
+          w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        } else {
+          const __half2 hh = __floats2half2_rn(vals[2 * q], vals[2 * q + 1]);
+          w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
       }
       *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -376,11 +386,11 @@ static int finish_irb(const GenLayer& y) {  // input rows per CTA: ~4+ blocks pe
 size_t last_finish_smem(const GenLayer& y) { return finish_smem_for(y, finish_irb(y)); }
 
 int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
-                       float inv_sigma2, float* loss, void* gcol, cudaStream_t stream) {
+                       float inv_sigma2, float gscale, float* loss, void* gcol, cudaStream_t stream) {
   FinishArgs a{};
   a.Y = Y; a.bias = y.bias; a.x = x; a.xhat = xhat; a.loss = loss; a.gcol = gcol;
   a.Hi = y.Hin; a.Wi = y.Win; a.Ho = y.Hout; a.Wo = y.Wout; a.k = y.k; a.stride = y.stride; a.pad = y.pad;
-  a.nc = y.cout; a.np = y.np_sc; a.inv_sigma2 = inv_sigma2;
+  a.nc = y.cout; a.np = y.np_sc; a.inv_sigma2 = inv_sigma2; a.gscale = gscale;
   a.irb = finish_irb(y);
   a.nblk = ceil_div(y.Hin, a.irb);
   const size_t smem = finish_smem_for(y, a.irb);
@@ -391,6 +401,11 @@ int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, 
     return DAMC_OK;
   };
   const bool same = y.k == 3 && y.stride == 1 && y.pad == 1, up = y.k == 4 && y.stride == 2 && y.pad == 1;
+  if (precision == DAMC_PREC_FP16) {
+    if (same) return go(last_finish_kernel<__half, 3, 1>);
+    if (up) return go(last_finish_kernel<__half, 4, 2>);
+    return go(last_finish_kernel<__half, 0, 0>);
+  }
   if (precision == DAMC_PREC_BF16) {
     if (same) return go(last_finish_kernel<__nv_bfloat16, 3, 1>);
     if (up) return go(last_finish_kernel<__nv_bfloat16, 4, 2>);
@@ -411,7 +426,9 @@ __global__ void stage_z_kernel(const float* __restrict__ z, T* __restrict__ zin,
 
 int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int precision, cudaStream_t stream) {
   const int n = B * nz_p;
-  if (precision == DAMC_PREC_BF16)
+  if (precision == DAMC_PREC_FP16)
+    stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<__half*>(zin), B, nz, nz_p);
+  else if (precision == DAMC_PREC_BF16)
     stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<__nv_bfloat16*>(zin), B, nz, nz_p);
   else
     stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<float*>(zin), B, nz, nz_p);

@@ -15,6 +15,7 @@
 //               bias / LeakyReLU / mask / tanh-likelihood, 16-byte stores).  Persistent CTAs, one per SM, static tile
 //               order with the N tiles of one M tile adjacent (A re-reads hit L2).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "damc_common.cuh"
@@ -200,6 +201,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// two fp32 -> one packed word of the operand type (uniform branch on the launch's precision)
+__device__ __forceinline__ uint32_t pack2(bool fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
 
 // ---- epilogue for one row x 16 consecutive columns ---------------------------------------------------------------------
 struct RowCtx {
@@ -223,8 +230,8 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
       float h2 = __uint_as_float(raw[4 * q + 2]) + bb.z, h3 = __uint_as_float(raw[4 * q + 3]) + bb.w;
       h0 = h0 > 0.f ? h0 : e.slope * h0; h1 = h1 > 0.f ? h1 : e.slope * h1;
       h2 = h2 > 0.f ? h2 : e.slope * h2; h3 = h3 > 0.f ? h3 : e.slope * h3;
-      w[2 * q] = pack_bf16x2(h0, h1);
-      w[2 * q + 1] = pack_bf16x2(h2, h3);
+      w[2 * q] = pack2(p.op_fp16, h0, h1);
+      w[2 * q + 1] = pack2(p.op_fp16, h2, h3);
     }
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o);
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -253,7 +260,7 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
         const uint32_t lo = aw[q] & 0xffffu, hi = aw[q] >> 16;
         const float s0 = (lo != 0u && lo < 0x8000u) ? 1.f : e.slope;
         const float s1 = (hi != 0u && hi < 0x8000u) ? 1.f : e.slope;
-        w[q] = pack_bf16x2(__uint_as_float(raw[8 * hlf + 2 * q]) * s0, __uint_as_float(raw[8 * hlf + 2 * q + 1]) * s1);
+        w[q] = pack2(p.op_fp16, __uint_as_float(raw[8 * hlf + 2 * q]) * s0, __uint_as_float(raw[8 * hlf + 2 * q + 1]) * s1);
       }
       dst[hlf] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -269,8 +276,10 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
   }
 #pragma unroll 1
   for (int j = 0; j < 16; ++j)
-    if (n0 + j < p.N)
-      epilogue_elem<__nv_bfloat16>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+    if (n0 + j < p.N) {
+      if (p.op_fp16) epilogue_elem<__half>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+      else epilogue_elem<__nv_bfloat16>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+    }
 }
 
 // ---- staged epilogue: TMEM -> registers -> (bias+LeakyReLU | mask) -> swizzled smem -> coalesced 16-byte row stores ------
@@ -365,7 +374,7 @@ struct StagedEpi {
             float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
             if (!((mword >> (8 * g + 2 * t2)) & 1u)) g0 *= e.slope;
             if (!((mword >> (8 * g + 2 * t2 + 1)) & 1u)) g1 *= e.slope;
-            w[t2] = pack_bf16x2(g0, g1);
+            w[t2] = pack2(p.op_fp16, g0, g1);
           }
         } else if (is_mask) {
           uint32_t aw[4];
@@ -376,7 +385,7 @@ struct StagedEpi {
             float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
             if ((int)(aw[t2] << 16) <= 0) g0 *= e.slope;
             if ((int)aw[t2] < 0x10000) g1 *= e.slope;
-            w[t2] = pack_bf16x2(g0, g1);
+            w[t2] = pack2(p.op_fp16, g0, g1);
           }
         } else {
           const float4* bp = reinterpret_cast<const float4*>(e.bias + ((n_base + c + 8 * g) % e.bias_mod));
@@ -387,7 +396,7 @@ struct StagedEpi {
             float h0 = __uint_as_float(v[8 * g + 2 * t2]) + bb[2 * t2], h1 = __uint_as_float(v[8 * g + 2 * t2 + 1]) + bb[2 * t2 + 1];
             if (h0 > 0.f) oword |= 1u << (8 * g + 2 * t2); else h0 *= e.slope;
             if (h1 > 0.f) oword |= 1u << (8 * g + 2 * t2 + 1); else h1 *= e.slope;
-            w[t2] = pack_bf16x2(h0, h1);
+            w[t2] = pack2(p.op_fp16, h0, h1);
           }
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
@@ -711,7 +720,7 @@ static EncodeTiledFn get_encode() {
 
 int tc_available() { return get_encode() != nullptr; }
 
-int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
+int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
   EncodeTiledFn enc = get_encode();
   if (!enc) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   if (p.Cs % TC_BK) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, TC_BK);
@@ -721,6 +730,9 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: merged parity classes need the k4-s2-p1 forward shape");
   TcParams P{};
   P.plan = p;
+  const bool fp16 = precision == DAMC_PREC_FP16;
+  P.plan.op_fp16 = fp16 ? 1 : 0;
+  const CUtensorMapDataType tm_dtype = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   P.BN = p.Np < 256 ? p.Np : 256;
   P.n_tiles = ceil_div(p.Np, P.BN);
   if (p.Hm * p.Wm >= TC_BM) {
@@ -763,7 +775,8 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
   P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
+  const uint32_t opfmt = fp16 ? 0u : 1u;  // kind::f16 operand format: 0 = f16, 1 = bf16
+  P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
 
   CUtensorMap tmA, tmB;
   {
@@ -774,7 +787,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     const cuuint64_t strides[4] = {row, row * p.Wm, row * p.Wm * p.Hm, plane_bytes};
     const cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)p.Wm, (cuuint32_t)P.Ht, (cuuint32_t)P.Bt, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p.A), dims, strides, box, estr,
+    const CUresult r = enc(&tmA, tm_dtype, 5, const_cast<void*>(p.A), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (Cs=%d W=%d H=%d B=%d planes=%d)", (int)r, p.Cs, p.Wm, p.Hm, p.B, nplanes);
@@ -784,7 +797,7 @@ int launch_gemm_tc(const GemmPlan& p, cudaStream_t stream) {
     const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(P.BN / cg)};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
+    const CUresult r = enc(&tmB, tm_dtype, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d (Cs=%d rows=%d BN=%d)", (int)r, p.Cs, p.ntaps * p.Np, P.BN);

@@ -22,12 +22,13 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check
 
-_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 DEFAULT_PRECISION = "fp32"
 
 
 def set_default_precision(name):
-    """'fp32' (CUDA-core fp32 GEMMs, rel 1e-3 parity) or 'bf16' (tcgen05 tensor cores, rel 2e-2)."""
+    """'fp32' (CUDA-core fp32 GEMMs, rel 1e-3 parity), 'bf16' (tcgen05 tensor cores, rel 2e-2) or 'fp16' (same
+    tensor-core engine with fp16 operands: ~8x smaller operand rounding at the same speed)."""
     global DEFAULT_PRECISION
     if name not in _PRECISIONS:
         raise ValueError(f"precision must be one of {list(_PRECISIONS)}")

@@ -33,7 +33,9 @@ enum { DAMC_OK = 0, DAMC_ERR_INVALID = 1, DAMC_ERR_UNSUPPORTED = 2, DAMC_ERR_CUD
 /* arithmetic of the generator GEMMs (the EBM, the update and the denoiser are always fp32) */
 enum {
   DAMC_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM: the rel-1e-3 parity mode                      */
-  DAMC_PREC_BF16 = 1  /* bf16 operands, fp32 accumulate on tcgen05/TMEM fed by TMA: the throughput mode */
+  DAMC_PREC_BF16 = 1, /* bf16 operands, fp32 accumulate on tcgen05/TMEM fed by TMA: the throughput mode */
+  DAMC_PREC_FP16 = 2  /* same engine with fp16 operands (8x finer operand rounding than bf16, same speed); the
+                         gradient chain is carried scaled by sigma^2 so that it stays inside the fp16 range */
 };
 
 int damc_version(void);
