@@ -330,3 +330,40 @@ def test_toy_amortizer_golden(dev):
     err = relmax(z, g["q_z_f32"])
     print(f"toy amortizer: ours-vs-reference-fp32 {err:.3e}")
     assert err < 5e-3, err
+
+
+@pytest.mark.parametrize("dataset,nz,ngf,nc,B", [("cifar10", 128, 64, 3, 1), ("cifar10", 128, 64, 3, 7), ("cifar10", 128, 64, 3, 129),
+                                                 ("svhn", 100, 64, 3, 37), ("mnist", 8, 64, 1, 131),
+                                                 ("celeba64", 100, 64, 3, 5)])
+def test_tensor_core_engine_matches_cuda_core_engine_on_ragged_batches(dataset, nz, ngf, nc, B, dev):
+    """Same bf16 tensors, two engines: tcgen05 (CTA pairs, merged classes, bit masks, partial tiles, odd tile counts)
+    against the CUDA-core kernel instantiated for bf16 storage (DAMC_TC=0).  Both accumulate the same bf16 products in
+    fp32, so z after a few steps must agree far inside the bf16-vs-fp64 error."""
+    import os
+    from damc_b200 import MCMC
+    K, sigma = 3, 0.3
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=13, gain=0.0)
+    outs = {}
+    for tag, env in (("tc", None), ("simt", "0")):
+        G, E = _nets(dataset, nz, ngf, nc, gsd, esd, dev)  # fresh modules: the engine is chosen when weights are packed
+        if env is None:
+            os.environ.pop("DAMC_TC", None)
+        else:
+            os.environ["DAMC_TC"] = env
+        try:
+            z = z0.to(dev).clone().requires_grad_(True)
+            outs[tag] = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, True, 0.1,
+                                                               noise=noise.to(dev), precision="bf16").cpu()
+            xh = MCMC.generator_forward(G, outs[tag].to(dev), precision="bf16").cpu()
+            outs[tag + "_x"] = xh
+        finally:
+            os.environ.pop("DAMC_TC", None)
+    gen = synth.gen_list_from_state(gsd, layers, torch.float64)
+    ebm = synth.ebm_list_from_state(esd, torch.float64)
+    ref = O.langevin_posterior_analytic(z0.double(), x.double(), gen, ebm, K, sigma, True, 0.1, noise.double())
+    e_tc, e_simt, e_pair = relmax(outs["tc"], ref), relmax(outs["simt"], ref), relmax(outs["tc"], outs["simt"])
+    print(f"{dataset} B={B}: tc-vs-fp64 {e_tc:.2e} simt-vs-fp64 {e_simt:.2e} tc-vs-simt {e_pair:.2e}")
+    assert e_tc < 2e-2 and e_simt < 2e-2
+    assert e_pair < max(2e-4, 0.5 * e_tc)
+    assert relmax(outs["tc_x"], outs["simt_x"]) < 2e-2
