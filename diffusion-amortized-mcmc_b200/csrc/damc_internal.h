@@ -37,9 +37,23 @@ int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStrea
 // Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]
 // with m = (b,y,x) on an Hm x Wm grid, and A_t[m,:] = src[plane_t][b, y+dy_t, x+dx_t, :] (zero outside the grid).
 enum LayerType { L_FIRST = 0, L_UP = 1, L_SAME = 2 };  // 1x1->kxk (s1,p0) | k4,s2,p1 | k3,s1,p1
-enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3, EPI_STORE_F32 = 4 };
+enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3, EPI_STORE_F32 = 4,
+               EPI_DEN_LAYER = 5, EPI_DEN_FINAL = 6 };
 
 struct Tap { signed char plane, dy, dx, pad; };
+
+// DAMC denoiser layer on the tcgen05 engine: the GEMM's columns come in quads (gate, hyper-bias, main, skip) per output
+// feature n; the epilogue forms out = (main+b) sigmoid(gate+bg) + hb + skip + bs  (reference diffusion_net.py:439-445).
+struct DenEpi {
+  const float* bias4;          // [4*dout] interleaved (bg, 0, b, bs)
+  void* dst1; int ld1, off1;   // leaky_relu(out, .01) -> dst1[b*ld1 + off1 + n]   (operand type)
+  void* dst2; int ld2, off2;   // second destination (U-net skip), or null
+  // EPI_DEN_FINAL: eps = z + out ; reverse update of z (reference diffusion_net.py:610-620)
+  float* z; float* eps_out; const float* noise;
+  int nz, residual, last, use_philox;
+  float c_pred, c_eps, c_zt, c_x, c_std;
+  unsigned long long seed, chain0, step;
+};
 
 struct Epilogue {
   int kind;
@@ -63,6 +77,7 @@ struct Epilogue {
   float* loss;          // null or scalar accumulator: sum (xhat-x)^2 * inv_sigma2/2
   void* gcol;           // im2col'd dL/dh_last for the last layer's dgrad: [B*Hi*Wi][64], slot (kh*k+kw)*4 + c
   int nc, k, stride, padding, Hi, Wi, Ho, Wo;
+  DenEpi den;           // EPI_DEN_LAYER / EPI_DEN_FINAL
   // EPI_DGRAD_Z / EPI_STORE_F32
   int nz_out;           // row stride of the fp32 output: [split][B][nz_out] partial sums, or [M][nz_out] raw accumulators
 };
@@ -134,6 +149,12 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws);
 int launch_gemm_simt(const GemmPlan& p, int precision, cudaStream_t stream);
 // tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate) -- gen_tc.cu
 int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream);
+// prepared launches (tensor maps encoded once, replayed many times; the plan's epilogue scalars stay editable)
+struct TcLaunch;
+int tc_prepare(const GemmPlan& p, int precision, TcLaunch** out);
+GemmPlan* tc_plan(TcLaunch* l);
+int tc_launch(TcLaunch* l, cudaStream_t stream);
+void tc_free(TcLaunch* l);
 int tc_available();
 
 // weight packing -- gen_pack.cu
@@ -150,5 +171,56 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
                       float* xhat, float* loss, cudaStream_t stream);
 float generator_grad_scale(const GenPack* g, float sigma);
 int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream);
+
+// ---- DAMC denoiser (Diffusion_UnetA, reference diffusion_net.py:463-533) ---------------------------------------------
+constexpr int DEN_LAYERS = 7;
+constexpr int DEN_TM = 16;        // chains per CTA (fp32 streaming kernel)
+constexpr int DEN_THREADS = 256;  // = max dout
+constexpr int DEN_MAXW = 512;     // widest layer input (concat of two 64*nf halves)
+
+// tcgen05 operands of one precision (bf16 | fp16): per layer one K-major weight matrix whose rows come in quads
+// (gate, hyper-bias, main, skip) per output feature and whose K axis is [layer input (din) | ctx activation (dout)].
+struct DenTcPack {
+  void* slab = nullptr;
+  void* Wq[DEN_LAYERS];      // [4*dout][din+dout]  operand type
+  float* bias4[DEN_LAYERS];  // [4*dout]            (bg, 0, b, bs)
+};
+
+struct DenPack : damc_handle {
+  int nz = 0, nxemb = 0, ntemb = 0, residual = 0, csum = 0;
+  int din[DEN_LAYERS], dout[DEN_LAYERS], coff[DEN_LAYERS];
+  float* slab = nullptr;
+  // device pointers into slab
+  float *tw1, *tb1, *tw2, *tb2, *Bp;          // time_mlp, B [nz][nz/2]
+  float* WcT_t;                               // [ntemb][csum]   (transposed temb half of all ctx Linears)
+  float* WcT_x;                               // [nxemb][csum]   (transposed xemb half)
+  float* bc;                                  // [csum]
+  float* Wms[DEN_LAYERS];                     // [din][dout][2]  interleaved (main, skip), transposed
+  float* Wgb[DEN_LAYERS];                     // [dout][dout][2] interleaved (gate, hyper-bias), transposed
+  float* bias3[DEN_LAYERS];                   // [3][dout]: b_main, b_skip, b_gate
+  int rows_gb[DEN_LAYERS], rows_ms[DEN_LAYERS], R[DEN_LAYERS];  // padded streamed rows / rows per 32 KB chunk
+  float* wstream = nullptr;                   // [Wgb_0 | Wms_0 | Wgb_1 | ...] in consumption order (inside slab)
+  size_t stream_floats = 0;
+  damc_denoiser_desc src;                     // caller's tensors (for damc_repack)
+  mutable DenTcPack* tc[3] = {nullptr, nullptr, nullptr};  // indexed by DAMC_PREC_*; built on first use, refilled by refill()
+  ~DenPack() override;
+  int refill(cudaStream_t stream) override;
+};
+
+struct DenWs {   // carved out of the caller's workspace
+  float *cx, *ct, *dlog, *coef;
+  void* A[DEN_LAYERS];   // tcgen05 mode: layer operands [B][din+dout] (operand type); null in fp32 mode
+  size_t bytes;
+};
+DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base);
+
+// denoiser_tc.cu: the 7 layers of one reverse step as tcgen05 GEMMs (quad-column epilogue), all T steps
+int den_tc_ensure(const DenPack* d, int precision, cudaStream_t stream);
+int den_tc_refill(const DenPack* d, int precision, cudaStream_t stream);
+void den_tc_free(DenTcPack* t);
+// coef: host table [nsteps][8] in execution order (c_pred, c_eps, c_zt, c_x, c_std, last)
+int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
+               const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
+               cudaStream_t stream);
 
 }  // namespace damc

@@ -22,31 +22,6 @@
 
 namespace damc {
 
-constexpr int DEN_LAYERS = 7;
-constexpr int DEN_TM = 16;        // chains per CTA
-constexpr int DEN_THREADS = 256;  // = max dout
-constexpr int DEN_MAXW = 512;     // widest layer input (concat of two 64*nf halves)
-
-struct DenPack : damc_handle {
-  int nz = 0, nxemb = 0, ntemb = 0, residual = 0, csum = 0;
-  int din[DEN_LAYERS], dout[DEN_LAYERS], coff[DEN_LAYERS];
-  float* slab = nullptr;
-  // device pointers into slab
-  float *tw1, *tb1, *tw2, *tb2, *Bp;          // time_mlp, B [nz][nz/2]
-  float* WcT_t;                               // [ntemb][csum]   (transposed temb half of all ctx Linears)
-  float* WcT_x;                               // [nxemb][csum]   (transposed xemb half)
-  float* bc;                                  // [csum]
-  float* Wms[DEN_LAYERS];                     // [din][dout][2]  interleaved (main, skip), transposed
-  float* Wgb[DEN_LAYERS];                     // [dout][dout][2] interleaved (gate, hyper-bias), transposed
-  float* bias3[DEN_LAYERS];                   // [3][dout]: b_main, b_skip, b_gate
-  int rows_gb[DEN_LAYERS], rows_ms[DEN_LAYERS], R[DEN_LAYERS];  // padded streamed rows / rows per 32 KB chunk
-  float* wstream = nullptr;                   // [Wgb_0 | Wms_0 | Wgb_1 | ...] in consumption order (inside slab)
-  size_t stream_floats = 0;
-  damc_denoiser_desc src;                     // caller's tensors (for damc_repack)
-  ~DenPack() override { if (slab) cudaFree(slab); }
-  int refill(cudaStream_t stream) override;
-};
-
 // ---- packing ------------------------------------------------------------------------------------------------------
 __global__ void pack_interleave_T(const float* __restrict__ A, const float* __restrict__ Bm, int rows, int cols,
                                   float* __restrict__ dst) {  // A,B: [rows][cols] -> dst[cols][rows][2]
@@ -430,17 +405,23 @@ static int run_hoist_and_time(const DenPack* d, const float* xemb, int B, int T,
   return DAMC_OK;
 }
 
-struct DenWs { float *cx, *ct, *dlog, *coef; size_t bytes; };
-static DenWs den_ws(const DenPack* d, int B, int T, void* base) {
-  DenWs w;
+DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base) {
+  DenWs w{};
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 256); return base ? (float*)((char*)base + r) : nullptr; };
   w.cx = take(sizeof(float) * (size_t)B * d->csum);
   w.ct = take(sizeof(float) * (size_t)T * d->csum);
   w.dlog = take(sizeof(float) * (size_t)(T + 1));
   w.coef = take(sizeof(float) * 8 * (size_t)T);
+  for (int i = 0; i < DEN_LAYERS; ++i)
+    w.A[i] = is_tc_precision(precision) ? (void*)take(2 * (size_t)B * (d->din[i] + d->dout[i])) : nullptr;
   w.bytes = o;
   return w;
+}
+
+DenPack::~DenPack() {
+  if (slab) cudaFree(slab);
+  for (DenTcPack* t : tc) den_tc_free(t);
 }
 
 int DenPack::refill(cudaStream_t s) {
@@ -464,6 +445,13 @@ int DenPack::refill(cudaStream_t s) {
     DAMC_CUDA(cudaMemcpyAsync(bc + off, h->bc[i], sizeof(float) * dn, dd, s));
   }
   DAMC_CUDA(cudaGetLastError());
+  for (int prec = 0; prec < 3; ++prec)
+    if (tc[prec]) DAMC_TRY(den_tc_refill(this, prec, s));
+  return DAMC_OK;
+}
+
+static int check_den_precision(int precision) {
+  if (precision != DAMC_PREC_FP32 && !is_tc_precision(precision)) DAMC_FAIL(DAMC_ERR_INVALID, "denoiser: unknown precision %d", precision);
   return DAMC_OK;
 }
 
@@ -531,20 +519,21 @@ extern "C" int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* h
   return DAMC_OK;
 }
 
-extern "C" size_t damc_denoise_workspace_bytes(const damc_handle* den, int B, int T) {
+extern "C" size_t damc_denoise_workspace_bytes(const damc_handle* den, int B, int T, int precision) {
   if (!den || den->kind != H_DEN || B <= 0 || T <= 0) return 0;
-  return den_ws(static_cast<const DenPack*>(den), B, T, nullptr).bytes;
+  return den_ws(static_cast<const DenPack*>(den), B, T, precision, nullptr).bytes;
 }
 
 extern "C" int damc_denoise(const damc_handle* den, float* z, const float* xemb, int B, int T, const float* host_logsnr,
                             int var_type, int with_noise, const float* noise, uint64_t seed, uint64_t chain0,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+                            int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (!den || den->kind != H_DEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_denoise: not a denoiser handle");
   if (!z || !xemb || !host_logsnr || B <= 0 || T < 2) DAMC_FAIL(DAMC_ERR_INVALID, "damc_denoise: bad arguments (need T >= 2)");
   if (var_type != 0 && var_type != 1) DAMC_FAIL(DAMC_ERR_INVALID, "damc_denoise: var_type must be 0 ('small') or 1 ('large')");
+  DAMC_TRY(check_den_precision(precision));
   const DenPack* d = static_cast<const DenPack*>(den);
   cudaStream_t s = (cudaStream_t)stream;
-  const DenWs w = den_ws(d, B, T, workspace);
+  const DenWs w = den_ws(d, B, T, precision, workspace);
   if (!workspace || workspace_bytes < w.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   DAMC_TRY(run_hoist_and_time(d, xemb, B, T, host_logsnr, w.cx, w.ct, w.dlog, s));
   std::vector<float> coef(8 * (size_t)T, 0.f);
@@ -555,6 +544,8 @@ extern "C" int damc_denoise(const damc_handle* den, float* z, const float* xemb,
     if (!with_noise) c[4] = 0.f;
     c[5] = i == 0 ? 1.f : 0.f;
   }
+  if (is_tc_precision(precision))
+    return den_tc_run(d, precision, w, z, nullptr, B, T, T, coef.data(), noise, noise == nullptr, seed, chain0, s);
   DAMC_CUDA(cudaMemcpyAsync(w.coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice, s));
   DenStreamArgs a{};
   fill_stream_args(d, &a);
@@ -566,14 +557,19 @@ extern "C" int damc_denoise(const damc_handle* den, float* z, const float* xemb,
 }
 
 extern "C" int damc_denoiser_eps(const damc_handle* den, const float* z, const float* xemb, float logsnr, float* eps_out,
-                                 int B, void* workspace, size_t workspace_bytes, void* stream) {
+                                 int B, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (!den || den->kind != H_DEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_denoiser_eps: not a denoiser handle");
   if (!z || !xemb || !eps_out || B <= 0) DAMC_FAIL(DAMC_ERR_INVALID, "damc_denoiser_eps: bad arguments");
+  DAMC_TRY(check_den_precision(precision));
   const DenPack* d = static_cast<const DenPack*>(den);
   cudaStream_t s = (cudaStream_t)stream;
-  const DenWs w = den_ws(d, B, 1, workspace);
+  const DenWs w = den_ws(d, B, 1, precision, workspace);
   if (!workspace || workspace_bytes < w.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
   DAMC_TRY(run_hoist_and_time(d, xemb, B, 1, &logsnr, w.cx, w.ct, w.dlog, s));
+  if (is_tc_precision(precision)) {
+    const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    return den_tc_run(d, precision, w, const_cast<float*>(z), eps_out, B, 1, 1, zero8, nullptr, 0, 0, 0, s);
+  }
   DAMC_CUDA(cudaMemsetAsync(w.coef, 0, sizeof(float) * 8, s));
   DenStreamArgs a{};
   fill_stream_args(d, &a);

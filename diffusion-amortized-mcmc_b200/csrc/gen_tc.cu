@@ -208,6 +208,44 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 // two fp32 -> one packed word of the operand type (uniform branch on the launch's precision)
 __device__ __forceinline__ uint32_t pack2(bool fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
 
+// ---- DAMC denoiser epilogues (EPI_DEN_LAYER / EPI_DEN_FINAL) ------------------------------------------------------------
+// Accumulator columns come in quads (gate, hyper-bias, main, skip) per output feature; sb = this launch's bias quads
+// (bg, 0, b, bs) in shared memory.   out = (main + b) * sigmoid(gate + bg) + hyper_bias + skip + bs   (diffusion_net.py:439-445)
+__device__ __forceinline__ float den_out(const uint32_t* raw4, const float* sb4) {
+  const float4 bq = *reinterpret_cast<const float4*>(sb4);
+  const float gate = __uint_as_float(raw4[0]) + bq.x, hb = __uint_as_float(raw4[1]);
+  const float mainv = __uint_as_float(raw4[2]) + bq.z, skip = __uint_as_float(raw4[3]) + bq.w;
+  return fmaf(mainv, __fdividef(1.f, 1.f + __expf(-gate)), hb + skip);
+}
+// last layer, 4 features [f0, f0+4) of chain r.b:  eps = z + out (residual, :530-531); x0 prediction and ancestral update
+// of z (:610-620), fp32 throughout
+__device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, const float outv[4]) {
+  const long long zi = (long long)b * d.nz + f0;
+  const float4 z4 = *reinterpret_cast<const float4*>(d.z + zi);
+  const float zt[4] = {z4.x, z4.y, z4.z, z4.w};
+  float res[4];
+  float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool noisy = d.eps_out == nullptr && !d.last && d.c_std != 0.f;
+  if (noisy) {
+    if (d.noise) {
+      const float4 n4 = *reinterpret_cast<const float4*>(d.noise + zi);
+      nrm[0] = n4.x; nrm[1] = n4.y; nrm[2] = n4.z; nrm[3] = n4.w;
+    } else if (d.use_philox) {
+      philox_normal4(d.seed, d.chain0 + (unsigned long long)b, d.step, (uint32_t)(f0 >> 2), nrm);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float eps = d.residual ? zt[q] + outv[q] : outv[q];
+    const float pred = d.c_pred * (zt[q] - eps * d.c_eps);
+    float zn = d.last ? pred : d.c_zt * zt[q] + d.c_x * pred;
+    if (noisy) zn = fmaf(d.c_std, nrm[q], zn);
+    res[q] = d.eps_out ? eps : zn;
+  }
+  float* dstp = d.eps_out ? d.eps_out + zi : d.z + zi;
+  *reinterpret_cast<float4*>(dstp) = make_float4(res[0], res[1], res[2], res[3]);
+}
+
 // ---- epilogue for one row x 16 consecutive columns ---------------------------------------------------------------------
 struct RowCtx {
   bool ok;
@@ -466,6 +504,11 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) { if (CG == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS); else tmem_alloc(tmem_slot, TC_TMEM_COLS); }
+  const bool den_kind = P.plan.epi.kind == EPI_DEN_LAYER || P.plan.epi.kind == EPI_DEN_FINAL;
+  // denoiser launches: bias quads of the whole layer live in smem behind the per-warp staging tiles
+  float* den_bias = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) + EW * 2048);
+  if (den_kind)
+    for (int i = threadIdx.x; i < P.plan.Np; i += blockDim.x) den_bias[i] = __ldg(P.plan.epi.den.bias4 + i);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
@@ -660,6 +703,70 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int item = 0; item < nitems; ++item) do_item(item, ra);
         }
       }
+    } else if (den_kind) {
+      // ---- denoiser layer: quad-column epilogue, operand rows leave through a swizzled smem tile as 64-byte row pieces ----
+      const DenEpi& d = p.epi.den;
+      const bool fin = p.epi.kind == EPI_DEN_FINAL;
+      const int cols_w = P.BN / NG;  // accumulator columns of this warp (128 of the 256-wide tile)
+      const uint32_t my_stage = staging + (uint32_t)(warp - 2) * 2048u;  // [32 rows][64 B], 16-byte chunks XOR-swizzled
+      int it = 0;
+      for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
+        int nt, sp;
+        const RowCtx rc = row_ctx(tile, nt, sp);
+        const int as = it & 1;
+        mbar_wait(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = t_lane + (uint32_t)as * 256u + (uint32_t)(grp * cols_w);
+        const int n_w = nt * P.BN + grp * cols_w;  // first accumulator column of this warp
+#pragma unroll 1
+        for (int c = 0; c < cols_w; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          float o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = den_out(v + 4 * q, den_bias + n_w + c + 4 * q);
+          if (fin) {
+            if (rc.ok) {
+              den_final_quad(d, rc.b, (n_w + c) >> 2, o);
+              den_final_quad(d, rc.b, ((n_w + c) >> 2) + 4, o + 4);
+            }
+          } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a = o[2 * q], b = o[2 * q + 1];
+              a = a > 0.f ? a : 0.01f * a;
+              b = b > 0.f ? b : 0.01f * b;
+              w[q] = pack2(p.op_fp16, a, b);
+            }
+            const uint32_t addr = my_stage + (uint32_t)lane * 64u + (uint32_t)((((c >> 5) ^ (lane >> 1)) & 3) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(bar_tempty(as), 0u)); else mbar_arrive(bar_tempty(as)); }
+        if (!fin) {
+          const int f_w = n_w >> 2;  // first output feature of this warp's 32
+          const int nchunk = cols_w >> 5;  // 16-byte chunks per row piece (4 when cols_w = 128)
+          const int myb = rc.ok ? rc.b : -1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // 4 lanes cover one row's 64 contiguous bytes; 8 rows per instruction
+            const int R = i * 8 + (lane >> 2), j = lane & 3;
+            const int bR = __shfl_sync(0xffffffffu, myb, R);
+            const uint32_t src = my_stage + (uint32_t)R * 64u + (uint32_t)(((j ^ (R >> 1)) & 3) << 4);
+            uint4 o4;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "r"(src) : "memory");
+            if (bR >= 0 && j < nchunk) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.dst1) + (long long)bR * d.ld1 + d.off1 + f_w + 8 * j) = o4;
+              if (d.dst2)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.dst2) + (long long)bR * d.ld2 + d.off2 + f_w + 8 * j) = o4;
+            }
+          }
+          __syncwarp();
+        }
+      }
     } else {
       int it = 0;
       for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
@@ -720,7 +827,14 @@ static EncodeTiledFn get_encode() {
 
 int tc_available() { return get_encode() != nullptr; }
 
-int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
+struct TcLaunch {
+  CUtensorMap tmA, tmB;
+  TcParams P;
+  int ew, cg;
+  size_t smem;
+};
+
+static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   EncodeTiledFn enc = get_encode();
   if (!enc) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   if (p.Cs % TC_BK) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, TC_BK);
@@ -728,7 +842,8 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
   if (p.Wm > TC_BM) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: pixel-grid width %d > %d", p.Wm, TC_BM);
   if (p.ncls > 1 && (p.ncls != 4 || p.ntaps != 4 || p.ksplit != 1 || p.epi.kind != EPI_FWD_ACT || p.Np % 64))
     DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: merged parity classes need the k4-s2-p1 forward shape");
-  TcParams P{};
+  TcParams& P = L->P;
+  P = TcParams{};
   P.plan = p;
   const bool fp16 = precision == DAMC_PREC_FP16;
   P.plan.op_fp16 = fp16 ? 1 : 0;
@@ -771,14 +886,19 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
   if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
   P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
   const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
-  const int staging_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP + 128 : 0;
+  const bool den_kind = p.epi.kind == EPI_DEN_LAYER || p.epi.kind == EPI_DEN_FINAL;
+  if (den_kind && (P.BN != 256 || p.Np % 256 || p.ksplit != 1 || p.ncls > 1))
+    DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: denoiser epilogue needs 4*dout (%d) to be a multiple of 256", p.Np);
+  // per-warp staging tiles, then (denoiser) the layer's bias quads
+  const int staging_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP + 128 : den_kind ? ew * 2048 + p.Np * 4 + 128 : 0;
   P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
   const uint32_t opfmt = fp16 ? 0u : 1u;  // kind::f16 operand format: 0 = f16, 1 = bf16
   P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap& tmA = L->tmA;
+  CUtensorMap& tmB = L->tmB;
   {
     const int nplanes = [&] { int mx = 0; for (int t = 0; t < p.ntaps; ++t) mx = std::max(mx, (int)p.taps[t].plane); return mx + 1; }();
     const cuuint64_t dims[5] = {(cuuint64_t)p.Cs, (cuuint64_t)p.Wm, (cuuint64_t)p.Hm, (cuuint64_t)p.B, (cuuint64_t)nplanes};
@@ -802,7 +922,17 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d (Cs=%d rows=%d BN=%d)", (int)r, p.Cs, p.ntaps * p.Np, P.BN);
   }
-  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024 + staging_bytes;
+  L->smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4) + 16 + 1024 + staging_bytes;
+  L->ew = ew;
+  L->cg = cg;
+  return DAMC_OK;
+}
+
+int tc_launch(TcLaunch* L, cudaStream_t stream) {
+  const TcParams& P = L->P;
+  const GemmPlan& p = P.plan;
+  const size_t smem = L->smem;
+  const int ew = L->ew, cg = L->cg;
   static bool attr_set = false;
   if (!attr_set) {
     DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -827,14 +957,31 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, tmA, tmB, P));
+    DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, L->tmA, L->tmB, L->P));
     return DAMC_OK;
   }
   const int total = P.m_tiles * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
-  if (ew == 16) convgemm_tc_kernel<16, 1><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(tmA, tmB, P);
-  else convgemm_tc_kernel<8, 1><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(tmA, tmB, P);
+  if (ew == 16) convgemm_tc_kernel<16, 1><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(L->tmA, L->tmB, L->P);
+  else convgemm_tc_kernel<8, 1><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(L->tmA, L->tmB, L->P);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
+}
+
+
+int tc_prepare(const GemmPlan& p, int precision, TcLaunch** out) {
+  TcLaunch* L = new TcLaunch();
+  const int r = tc_prepare_into(p, precision, L);
+  if (r != DAMC_OK) { delete L; return r; }
+  *out = L;
+  return DAMC_OK;
+}
+GemmPlan* tc_plan(TcLaunch* l) { return &l->P.plan; }
+void tc_free(TcLaunch* l) { delete l; }
+
+int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream) {
+  TcLaunch L;
+  DAMC_TRY(tc_prepare_into(p, precision, &L));
+  return tc_launch(&L, stream);
 }
 
 }  // namespace damc

@@ -24,6 +24,7 @@ from ._lib import lib, check
 
 _PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 DEFAULT_PRECISION = "fp32"
+DEFAULT_DENOISER_PRECISION = "fp32"
 
 
 def set_default_precision(name):
@@ -33,6 +34,15 @@ def set_default_precision(name):
     if name not in _PRECISIONS:
         raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
     DEFAULT_PRECISION = name
+
+
+def set_default_denoiser_precision(name):
+    """Arithmetic of the DAMC denoiser GEMMs: 'fp32' (one persistent CUDA-core kernel for all T steps; parity mode) or
+    'bf16' / 'fp16' (per-layer tcgen05 GEMMs; the throughput mode for large batches of chains)."""
+    global DEFAULT_DENOISER_PRECISION
+    if name not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
+    DEFAULT_DENOISER_PRECISION = name
 
 
 def set_requires_grad(nets, requires_grad=False):
@@ -382,14 +392,18 @@ def logsnr_table(T, logsnr_min, logsnr_max):
     return (-2.0 * torch.log(torch.tan(a * t + b))).numpy().astype(np.float32)
 
 
-def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init=None, seed=None, chain0=0):
+def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init=None, seed=None, chain0=0,
+                precision=None, xemb=None):
     """DAMC ancestral sampler: z_T ~ N(0,I), T reverse steps of the latent denoiser, returns z_0 [b,nz].
     The image encoder / prior embedding run once in PyTorch; the T-step loop runs in libdamc_b200.
     noise: optional [T-1,b,nz] injected normals; z_init: optional z_T (otherwise torch.randn as the reference)."""
     if x is not None and cond_w is not None and cond_w > 0:
         raise NotImplementedError("classifier-free guidance (cond_w > 0) is never taken by the reference's callers")
+    prec = _PRECISIONS[precision or DEFAULT_DENOISER_PRECISION]
     with torch.no_grad():
-        if x is not None:
+        if xemb is not None:  # precomputed context embedding (skips the encoder / prior_emb)
+            b, device = len(xemb), xemb.device
+        elif x is not None:
             assert b is None and device is None
             b, device = len(x), x.device
             xemb = Q.encoder(x)
@@ -407,26 +421,27 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
     lam = logsnr_table(T, Q.logsnr_min, Q.logsnr_max)
     lam_c = (C.c_float * (T + 1))(*lam.tolist(), 0.0)
     var_type = {"small": 0, "large": 1}[Q.var_type]
-    nbytes = lib().damc_denoise_workspace_bytes(h.ptr, b, T)
+    nbytes = lib().damc_denoise_workspace_bytes(h.ptr, b, T, prec)
     ws = _workspace(device, nbytes)
     with torch.cuda.device(device):
         check(lib().damc_denoise(h.ptr, C.c_void_p(zt.data_ptr()), C.c_void_p(xemb.data_ptr()), b, T, lam_c, var_type,
                                  int(bool(Q.with_noise)), nptr,
                                  _draw_seed() if (seed is None and noise is None) else int(seed or 0), int(chain0),
-                                 C.c_void_p(ws.data_ptr()), nbytes, _stream(device)), "damc_denoise")
+                                 prec, C.c_void_p(ws.data_ptr()), nbytes, _stream(device)), "damc_denoise")
     return zt
 
 
-def denoiser_eps(Q, z, logsnr, xemb):
+def denoiser_eps(Q, z, logsnr, xemb, *, precision=None):
     """One eps-prediction Q.p(z, logsnr, xemb) with a batch-constant logsnr (float) through the CUDA library."""
     zd, xe = _f32_cuda(z, "z"), _f32_cuda(xemb, "xemb")
+    prec = _PRECISIONS[precision or DEFAULT_DENOISER_PRECISION]
     h = pack_denoiser(Q)
     out = torch.empty_like(zd)
-    nbytes = lib().damc_denoise_workspace_bytes(h.ptr, zd.shape[0], 1)
+    nbytes = lib().damc_denoise_workspace_bytes(h.ptr, zd.shape[0], 1, prec)
     ws = _workspace(zd.device, nbytes)
     with torch.cuda.device(zd.device):
         check(lib().damc_denoiser_eps(h.ptr, C.c_void_p(zd.data_ptr()), C.c_void_p(xe.data_ptr()), float(logsnr),
-                                      C.c_void_p(out.data_ptr()), zd.shape[0], C.c_void_p(ws.data_ptr()), nbytes,
+                                      C.c_void_p(out.data_ptr()), zd.shape[0], prec, C.c_void_p(ws.data_ptr()), nbytes,
                                       _stream(zd.device)), "damc_denoiser_eps")
     return out
 

@@ -41,9 +41,9 @@ SIGNATURES = {
     "damc_pack_toy_mlp": (_I, [C.POINTER(_P), _I, _I, _I, C.POINTER(_P), C.POINTER(_P), _P]),
     "damc_toy_posterior_langevin": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, _P, _U64, _U64, _U64, _P]),
     "damc_pack_denoiser": (_I, [C.POINTER(_P), C.POINTER(DenoiserDesc), _P]),
-    "damc_denoise_workspace_bytes": (_SZ, [_P, _I, _I]),
-    "damc_denoise": (_I, [_P, _P, _P, _I, _I, C.POINTER(_F), _I, _I, _P, _U64, _U64, _P, _SZ, _P]),
-    "damc_denoiser_eps": (_I, [_P, _P, _P, _F, _P, _I, _P, _SZ, _P]),
+    "damc_denoise_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "damc_denoise": (_I, [_P, _P, _P, _I, _I, C.POINTER(_F), _I, _I, _P, _U64, _U64, _I, _P, _SZ, _P]),
+    "damc_denoiser_eps": (_I, [_P, _P, _P, _F, _P, _I, _I, _P, _SZ, _P]),
     "damc_launch_count": (C.c_longlong, []),
     "damc_profile_enable": (_I, [_I]),
     "damc_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -207,9 +207,9 @@ class _netQ_U(nn.Module):
         self.xemb = nn.Parameter(torch.randn(1, nxemb), requires_grad=True)
         self.prior_emb = nn.Sequential(nn.Linear(nz, 128), nn.LeakyReLU(), nn.Linear(128, nxemb))
 
-    def forward(self, x=None, b=None, device=None, cond_w=-1, noise=None):
+    def forward(self, x=None, b=None, device=None, cond_w=-1, noise=None, precision=None):
         from . import MCMC  # late import: MCMC needs the CUDA library
-        return MCMC.damc_sample(self, x=x, b=b, device=device, cond_w=cond_w, noise=noise)
+        return MCMC.damc_sample(self, x=x, b=b, device=device, cond_w=cond_w, noise=noise, precision=precision)
 
     def calculate_loss(self, x=None, z=None, mask=None):
         """Denoising loss 0.5*|eps - eps_hat|^2 per sample at a random noise level (reference diffusion_net.py:624-646).

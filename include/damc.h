@@ -30,7 +30,8 @@ typedef struct damc_handle damc_handle; /* opaque packed-weight handle */
 
 enum { DAMC_OK = 0, DAMC_ERR_INVALID = 1, DAMC_ERR_UNSUPPORTED = 2, DAMC_ERR_CUDA = 3, DAMC_ERR_WORKSPACE = 4 };
 
-/* arithmetic of the generator GEMMs (the EBM, the update and the denoiser are always fp32) */
+/* arithmetic of the GEMM operands -- generator (chosen at pack time) and DAMC denoiser (chosen per call).  The EBM, the
+ * Langevin / reverse-step updates, z itself and every accumulator are always fp32. */
 enum {
   DAMC_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM: the rel-1e-3 parity mode                      */
   DAMC_PREC_BF16 = 1, /* bf16 operands, fp32 accumulate on tcgen05/TMEM fed by TMA: the throughput mode */
@@ -110,20 +111,24 @@ typedef struct {
 } damc_denoiser_desc;
 
 int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* host_desc, void* stream);
-size_t damc_denoise_workspace_bytes(const damc_handle* den, int B, int T);
+size_t damc_denoise_workspace_bytes(const damc_handle* den, int B, int T, int precision);
 
 /* z [B,nz] holds z_T on entry and z_0 on return; xemb [B,nxemb] is encoder(x) or prior_emb(randn).
  * host_logsnr[T+1]: lambda(t_i) for i = 0..T-1 then unused; computed by the caller exactly as the reference's
  *   logsnr_schedule_fn (fp32) so the time embedding sees the same argument.
  * var_type: 0 = 'small', 1 = 'large'.  noise: NULL -> Philox, else [T-1,B,nz] consumed in execution order.
- * The reference draws eps even when with_noise is false (:616); with injected noise that is immaterial.          */
+ * The reference draws eps even when with_noise is false (:616); with injected noise that is immaterial.
+ * precision: DAMC_PREC_FP32 = all T steps in ONE persistent fp32 kernel (z resident in shared memory, weights streamed
+ *   by cp.async.bulk); DAMC_PREC_BF16 / DAMC_PREC_FP16 = per step one operand-preparation kernel + 7 tcgen05/TMEM GEMMs
+ *   fed by TMA (each ConcatSquashLinearSkipCtx layer is one GEMM with a fused gate/bias/skip epilogue; the last one also
+ *   applies the reverse update).  Layer widths must be multiples of 64 in the tensor-core modes.                    */
 int damc_denoise(const damc_handle* den, float* z, const float* xemb, int B, int T, const float* host_logsnr,
-                 int var_type, int with_noise, const float* noise, uint64_t seed, uint64_t chain0, void* workspace,
-                 size_t workspace_bytes, void* stream);
+                 int var_type, int with_noise, const float* noise, uint64_t seed, uint64_t chain0, int precision,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* single eps-prediction of Q.p (reference src/diffusion_net.py:501-533) -- used by the per-step parity tests */
 int damc_denoiser_eps(const damc_handle* den, const float* z, const float* xemb, float logsnr, float* eps_out, int B,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------------------------
  * damc_launch_count : cumulative number of kernels this library has launched in the calling process.
