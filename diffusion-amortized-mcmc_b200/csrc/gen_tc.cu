@@ -28,8 +28,31 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 8, TC_TMEM_COLS = 512;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_STAGING_PER_WARP = 32 * 64 * 2;  // per epilogue warp: 32 rows x 64 bf16
 
+// n / d for 0 <= n < 2^31 without the ~25-instruction integer division: mul = ceil(2^(31+s) / d), s = ceil(log2 d)
+struct FastDiv {
+  uint32_t mul, shr;  // d == 1: mul = 0
+  int d;
+  __device__ __forceinline__ int div(int n) const {
+    return mul ? (int)((uint32_t)(((unsigned long long)(uint32_t)n * mul) >> 31) >> shr) : n;
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * d; }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) { f.mul = 0; f.shr = 0; f.d = 1; return f; }
+  uint32_t sh = 0;
+  while ((1u << sh) < (uint32_t)d) ++sh;
+  f.shr = sh;
+  f.mul = (uint32_t)((((unsigned long long)1 << (31 + sh)) + (unsigned long long)d - 1) / (unsigned long long)d);
+  return f;
+}
+
 struct TcParams {
   GemmPlan plan;
+  FastDiv fd_ntiles, fd_munits, fd_ncls, fd_tpi, fd_perimg, fd_wm, fd_bias;
+  const float* bias_src;   // bias vector copied into smem at kernel start (bias_floats > 0), at staging + bias_off bytes
+  int bias_floats, bias_off;
   int BN, stages, b_stage_bytes;
   int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
   int Ht, Bt, tiles_per_img, tile_rows;
@@ -389,7 +412,7 @@ struct StagedEpi {
   }
   // accumulators of one segment -> epilogue math -> smem -> global
   __device__ __forceinline__ void process(const GemmPlan& p, uint32_t t_seg, uint32_t my_stage, int lane, int n_base,
-                                          uint2 mw) const {
+                                          uint2 mw, const float* sbias /* smem bias + (n_base % bias_mod) */) const {
     const Epilogue& e = p.epi;
     const bool is_mask = e.kind == EPI_DGRAD_MASK;
     const bool bits = e.maskbits != nullptr;
@@ -409,10 +432,10 @@ struct StagedEpi {
         if (is_mask && bits) {
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
-            float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
-            if (!((mword >> (8 * g + 2 * t2)) & 1u)) g0 *= e.slope;
-            if (!((mword >> (8 * g + 2 * t2 + 1)) & 1u)) g1 *= e.slope;
-            w[t2] = pack2(p.op_fp16, g0, g1);
+            const float g0 = __uint_as_float(v[8 * g + 2 * t2]), g1 = __uint_as_float(v[8 * g + 2 * t2 + 1]);
+            const float s0 = (mword & (1u << (8 * g + 2 * t2))) ? 1.f : e.slope;       // select, not branch
+            const float s1 = (mword & (1u << (8 * g + 2 * t2 + 1))) ? 1.f : e.slope;
+            w[t2] = pack2(p.op_fp16, g0 * s0, g1 * s1);
           }
         } else if (is_mask) {
           uint32_t aw[4];
@@ -426,8 +449,8 @@ struct StagedEpi {
             w[t2] = pack2(p.op_fp16, g0, g1);
           }
         } else {
-          const float4* bp = reinterpret_cast<const float4*>(e.bias + ((n_base + c + 8 * g) % e.bias_mod));
-          const float4 b0v = __ldg(bp), b1v = __ldg(bp + 1);
+          const float4* bp = reinterpret_cast<const float4*>(sbias + c + 8 * g);
+          const float4 b0v = bp[0], b1v = bp[1];
           const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
@@ -505,10 +528,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   if (warp == 1) { if (CG == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS); else tmem_alloc(tmem_slot, TC_TMEM_COLS); }
   const bool den_kind = P.plan.epi.kind == EPI_DEN_LAYER || P.plan.epi.kind == EPI_DEN_FINAL;
-  // denoiser launches: bias quads of the whole layer live in smem behind the per-warp staging tiles
-  float* den_bias = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) + EW * 2048);
-  if (den_kind)
-    for (int i = threadIdx.x; i < P.plan.Np; i += blockDim.x) den_bias[i] = __ldg(P.plan.epi.den.bias4 + i);
+  // the launch's bias vector (forward: [Cout]; denoiser: bias quads of the whole layer) lives in smem behind the staging tiles
+  float* den_bias = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) + P.bias_off);
+  for (int i = threadIdx.x; i < P.bias_floats; i += blockDim.x) den_bias[i] = __ldg(P.bias_src + i);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
@@ -523,19 +545,21 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // tile -> (m tile, n tile, K split | parity class).  sp carries the split index, or the class when ncls > 1.
   auto decode = [&](int tile, int& mt, int& nt, int& sp) {
     if (ncls > 1 && P.cls_inner) {  // classes innermost: the 4 classes of one input window run back to back and share it through L2
-      sp = tile % ncls;
-      tile /= ncls;
-      nt = tile % P.n_tiles;
-      mt = (tile / P.n_tiles) * CG + (int)cta_rank;
+      int q;
+      P.fd_ncls.divmod(tile, q, sp);
+      int mu;
+      P.fd_ntiles.divmod(q, mu, nt);
+      mt = mu * CG + (int)cta_rank;
       return;
     }
-    nt = tile % P.n_tiles;
-    const int r = tile / P.n_tiles;
-    mt = (r % m_units) * CG + (int)cta_rank;   // this CTA's 128-row tile (may lie past the end: rows are masked)
-    sp = r / m_units;
+    int r;
+    P.fd_ntiles.divmod(tile, r, nt);
+    int mu;
+    P.fd_munits.divmod(r, sp, mu);
+    mt = mu * CG + (int)cta_rank;   // this CTA's 128-row tile (may lie past the end: rows are masked)
   };
   auto tile_origin = [&](int mt, int& b0, int& y0) {
-    if (P.Bt == 1) { b0 = mt / P.tiles_per_img; y0 = (mt - b0 * P.tiles_per_img) * P.Ht; }
+    if (P.Bt == 1) { int rem; P.fd_tpi.divmod(mt, b0, rem); y0 = rem * P.Ht; }
     else { b0 = mt * P.Bt; y0 = 0; }
   };
 
@@ -620,9 +644,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int per_img = P.Ht * p.Wm;
       int bt, rem, yy, xx;
       if (P.per_img_shift >= 0) { bt = r >> P.per_img_shift; rem = r & (per_img - 1); }
-      else { bt = r / per_img; rem = r - bt * per_img; }
+      else P.fd_perimg.divmod(r, bt, rem);
       if (P.wm_shift >= 0) { yy = rem >> P.wm_shift; xx = rem & (p.Wm - 1); }
-      else { yy = rem / p.Wm; xx = rem - yy * p.Wm; }
+      else P.fd_wm.divmod(rem, yy, xx);
       rc.b = b0 + bt;
       rc.y = y0 + yy;
       rc.x = xx;
@@ -654,24 +678,28 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       } else {
         const int nitems = ntl * nseg_w;
         uint4 ra[StagedEpi::NIT], rb[StagedEpi::NIT];
-        auto request = [&](uint4 (&r)[StagedEpi::NIT], int item) {
-          if (!is_mask || item >= nitems) return;
-          const int k = item / nseg_w, sg = item - k * nseg_w;
+        // (tile ordinal k, segment ordinal sg) of the current item and of the item whose rows are requested ahead
+        struct ItemPos { int k, sg; };
+        auto advance = [&](ItemPos& ip) { if (++ip.sg == nseg_w) { ip.sg = 0; ++ip.k; } };
+        auto request = [&](uint4 (&r)[StagedEpi::NIT], const ItemPos& ip) {
+          if (!is_mask || ip.k >= ntl) return;
           int nt, sp;
-          const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
-          const int n_base = nt * P.BN + (grp + NG * sg) * 64;
+          const RowCtx rc = row_ctx(unit + ip.k * nunits, nt, sp);
+          const int n_base = nt * P.BN + (grp + NG * ip.sg) * 64;
           if (n_base >= p.N) return;
           if (bits) { const uint2 mw = StagedEpi::load_mask_words(p, rc, n_base); r[0].x = mw.x; r[0].y = mw.y; }
           else se.request(r, StagedEpi::act_ptr_bits(p, rc), n_base);
         };
         constexpr int AHEAD = EW == 8 ? 2 : 1;  // 16 warps: one register set each (keeps the kernel spill-free)
-        request(ra, 0);
-        if (AHEAD == 2) request(rb, 1);
+        ItemPos cur{0, 0}, nxt{0, 0};
+        request(ra, nxt);
+        advance(nxt);
+        if (AHEAD == 2) { request(rb, nxt); advance(nxt); }
         int nt = 0, sp = 0;
-        // one (tile, segment) item; r holds its activation rows (requested two items ago) and is re-armed for item+2.
+        // one (tile, segment) item; r holds its activation rows (requested AHEAD items ago) and is re-armed for item+AHEAD.
         // The two register sets alternate (no register copies: a copy would wait on the loads it moves).
-        auto do_item = [&](int item, uint4 (&r)[StagedEpi::NIT]) {
-          const int k = item / nseg_w, sg = item - k * nseg_w;
+        auto do_item = [&](uint4 (&r)[StagedEpi::NIT]) {
+          const int k = cur.k, sg = cur.sg;
           const int as = k & 1;
           if (sg == 0) {
             const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
@@ -681,26 +709,33 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint2 mw = make_uint2(0u, 0u);
           if (is_mask) {
             if (bits) mw = make_uint2(r[0].x, r[0].y); else se.stash(r, my_stage);
-            request(r, item + AHEAD);
+            request(r, nxt);
+            advance(nxt);
           }
           if (sg == 0) {
             mbar_wait(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
             tc_fence_after();
           }
-          if (n_base < p.N) se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base, mw);
+          if (n_base < p.N) {
+            int bq, brem = 0;
+            if (!is_mask) P.fd_bias.divmod(n_base, bq, brem);
+            se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base, mw,
+                       (P.bias_floats ? den_bias : p.epi.bias) + brem);
+          }
           if (sg == nseg_w - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) release_acc(as);
           }
+          advance(cur);
         };
         if (AHEAD == 2) {
           for (int item = 0; item < nitems; item += 2) {
-            do_item(item, ra);
-            if (item + 1 < nitems) do_item(item + 1, rb);
+            do_item(ra);
+            if (item + 1 < nitems) do_item(rb);
           }
         } else {
-          for (int item = 0; item < nitems; ++item) do_item(item, ra);
+          for (int item = 0; item < nitems; ++item) do_item(ra);
         }
       }
     } else if (den_kind) {
@@ -870,12 +905,17 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.kb_per_split = ceil_div(P.kb_total, p.ksplit);
   if ((long long)P.kb_per_split * (p.ksplit - 1) >= P.kb_total)
     DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: ksplit %d leaves an empty K range (%d blocks)", p.ksplit, P.kb_total);
+  P.fd_ntiles = make_fastdiv(P.n_tiles);
+  P.fd_ncls = make_fastdiv(p.ncls > 1 ? p.ncls : 1);
+  P.fd_tpi = make_fastdiv(P.tiles_per_img);
+  P.fd_perimg = make_fastdiv(P.Ht * p.Wm);
+  P.fd_wm = make_fastdiv(p.Wm);
   P.a_box_bytes = (uint32_t)P.tile_rows * TC_BK * 2;
   P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
   P.stage_cols = 0;
   P.cls_inner = getenv("DAMC_TC_CLS_OUTER") ? 0 : 1;
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
-    if (P.BN % 64 == 0 && p.N % 64 == 0) P.stage_cols = 64;
+    if (P.BN % 64 == 0 && p.N % 64 == 0 && (p.epi.kind != EPI_FWD_ACT || p.epi.bias_mod % 64 == 0)) P.stage_cols = 64;
   }
   if (!P.stage_cols && p.epi.maskbits != nullptr && (p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK))
     DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: bit masks need the staged epilogue (N %% 64 == 0); set DAMC_TC_NOBITS=1");
@@ -883,6 +923,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   // CTA-pair MMA for the MMA-bound launches: full 256-wide N tiles, long K, an even grid of pairs
   static const bool allow_2sm = []{ const char* e = getenv("DAMC_TC_2SM"); return !(e && e[0] == '0'); }();
   const int cg = (allow_2sm && ew == 8 && P.BN == 256 && p.Np % 256 == 0 && P.kb_per_split >= 16 && P.m_tiles >= 2) ? 2 : 1;
+  P.fd_munits = make_fastdiv(ceil_div(P.m_tiles, cg));
   if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
   P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
   const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
@@ -890,8 +931,21 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   if (den_kind && (P.BN != 256 || p.Np % 256 || p.ksplit != 1 || p.ncls > 1))
     DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: denoiser epilogue needs 4*dout (%d) to be a multiple of 256", p.Np);
   // per-warp staging tiles, then (denoiser) the layer's bias quads
-  const int staging_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP + 128 : den_kind ? ew * 2048 + p.Np * 4 + 128 : 0;
-  P.stages = std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - staging_bytes) / stage_bytes));
+  P.bias_src = nullptr;
+  P.bias_floats = 0;
+  P.bias_off = 0;
+  P.fd_bias = make_fastdiv(1);
+  if (den_kind) { P.bias_src = p.epi.den.bias4; P.bias_floats = p.Np; P.bias_off = ew * 2048; }
+  else if (P.stage_cols && p.epi.kind == EPI_FWD_ACT) {
+    P.bias_src = p.epi.bias; P.bias_floats = p.epi.bias_mod; P.bias_off = ew * TC_STAGING_PER_WARP;
+    P.fd_bias = make_fastdiv(p.epi.bias_mod);
+  }
+  const int tiles_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP : den_kind ? ew * 2048 : 0;
+  auto stages_for = [&](int sb) { return std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - sb) / stage_bytes)); };
+  if (!den_kind && stages_for(tiles_bytes + P.bias_floats * 4 + 128) < stages_for(tiles_bytes + 128))
+    P.bias_floats = 0;  // a pipeline stage is worth more than the smem bias: the epilogue reads the bias through L1 instead
+  const int staging_bytes = tiles_bytes + P.bias_floats * 4 + 128;
+  P.stages = stages_for(staging_bytes);
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
   const uint32_t opfmt = fp16 ? 0u : 1u;  // kind::f16 operand format: 0 = f16, 1 = bf16
