@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(256) den_prep_kernel(const DenPrepArgs a, int 
   extern __shared__ __align__(16) float sm[];
   const int nz = a.nz, half = nz >> 1;
   const bool fp16 = a.fp16 != 0;
+  // programmatic dependent launch: the first layer's GEMM may set up now; this kernel waits for the previous step's
+  // last layer (which wrote z) before reading anything
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((int)blockIdx.x < nb_embed) {
     float* Bs = sm;               // [nz][half]
     float* zs = sm + nz * half;   // [EMB_CHAINS][nz]
@@ -230,7 +234,19 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
   for (int st = 0; st < nsteps; ++st) {
     const int irev = eps_out ? 0 : T - 1 - st;
     pa.ctrow = w.ct + (size_t)irev * d->csum;
-    den_prep_kernel<<<nb_embed + nb_ctx, 256, prep_smem, s>>>(pa, nb_embed);
+    {
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.gridDim = dim3(nb_embed + nb_ctx);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = prep_smem;
+      cfg.stream = s;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      DAMC_CUDA(cudaLaunchKernelEx(&cfg, den_prep_kernel, pa, nb_embed));
+    }
     const float* cf = host_coef + 8 * (size_t)st;
     DenEpi& e = tc_plan(L[DEN_LAYERS - 1])->epi.den;
     e.c_pred = cf[0]; e.c_eps = cf[1]; e.c_zt = cf[2]; e.c_x = cf[3]; e.c_std = cf[4];

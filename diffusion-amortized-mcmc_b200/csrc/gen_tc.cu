@@ -515,6 +515,9 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  // Programmatic dependent launch: let the next kernel of the stream begin its own prologue now; it (like this kernel,
+  // below) blocks in griddepcontrol.wait until its predecessor has completed and flushed before touching any tensor.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // MMA unit (CTA or CTA pair)
@@ -530,6 +533,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const bool den_kind = P.plan.epi.kind == EPI_DEN_LAYER || P.plan.epi.kind == EPI_DEN_FINAL;
   // the launch's bias vector (forward: [Cout]; denoiser: bias quads of the whole layer) lives in smem behind the staging tiles
   float* den_bias = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) + P.bias_off);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
   for (int i = threadIdx.x; i < P.bias_floats; i += blockDim.x) den_bias[i] = __ldg(P.bias_src + i);
   tc_fence_before();
   __syncthreads();
@@ -884,6 +888,11 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.plan.op_fp16 = fp16 ? 1 : 0;
   const CUtensorMapDataType tm_dtype = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   P.BN = p.Np < 256 ? p.Np : 256;
+  const bool den_kind = p.epi.kind == EPI_DEN_LAYER || p.epi.kind == EPI_DEN_FINAL;
+  if (den_kind) {
+    // few chains: narrower N tiles spread one layer over more SMs and shorten each CTA's serial load -> MMA -> epilogue chain
+    while (P.BN > 64 && (long long)ceil_div(p.B, TC_BM) * (p.Np / P.BN) < 96) P.BN /= 2;
+  }
   P.n_tiles = ceil_div(p.Np, P.BN);
   if (p.Hm * p.Wm >= TC_BM) {
     P.Bt = 1;
@@ -927,8 +936,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
   P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
   const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
-  const bool den_kind = p.epi.kind == EPI_DEN_LAYER || p.epi.kind == EPI_DEN_FINAL;
-  if (den_kind && (P.BN != 256 || p.Np % 256 || p.ksplit != 1 || p.ncls > 1))
+  if (den_kind && (P.BN % 64 || p.Np % P.BN || p.ksplit != 1 || p.ncls > 1))
     DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: denoiser epilogue needs 4*dout (%d) to be a multiple of 256", p.Np);
   // per-warp staging tiles, then (denoiser) the layer's bias quads
   P.bias_src = nullptr;
@@ -1000,24 +1008,35 @@ int tc_launch(TcLaunch* L, cudaStream_t stream) {
     DAMC_CUDA(cudaGetDevice(&dev));
     DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  static const bool use_pdl = []{ const char* e = getenv("DAMC_TC_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
   if (cg == 2) {
     const int units = ceil_div(P.m_tiles, 2) * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
-    cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * std::min(units, num_sms / 2));
     cfg.blockDim = dim3(64 + 32 * 8);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.numAttrs = na;
     DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, L->tmA, L->tmB, L->P));
     return DAMC_OK;
   }
   const int total = P.m_tiles * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
-  if (ew == 16) convgemm_tc_kernel<16, 1><<<std::min(total, num_sms), 64 + 32 * 16, smem, stream>>>(L->tmA, L->tmB, L->P);
-  else convgemm_tc_kernel<8, 1><<<std::min(total, num_sms), 64 + 32 * 8, smem, stream>>>(L->tmA, L->tmB, L->P);
-  DAMC_CUDA(cudaGetLastError());
+  cfg.gridDim = dim3(std::min(total, num_sms));
+  cfg.blockDim = dim3(64 + 32 * ew);
+  cfg.numAttrs = na;
+  if (ew == 16) DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<16, 1>, L->tmA, L->tmB, L->P));
+  else DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 1>, L->tmA, L->tmB, L->P));
   return DAMC_OK;
 }
 
