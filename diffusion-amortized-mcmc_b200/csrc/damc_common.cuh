@@ -39,7 +39,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- handle kinds ------------------------------------------------------------------------------------------------
-enum HandleKind { H_MLP = 1, H_GEN = 2, H_TOY = 3, H_DEN = 4 };
+enum HandleKind { H_MLP = 1, H_GEN = 2, H_TOY = 3, H_DEN = 4, H_ENC = 5 };
 
 // ---- Philox4x32-10 (counter-based; shard-invariant: keyed by GLOBAL chain index and step) -------------------------
 __host__ __device__ inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,

@@ -38,7 +38,7 @@ int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStrea
 // with m = (b,y,x) on an Hm x Wm grid, and A_t[m,:] = src[plane_t][b, y+dy_t, x+dx_t, :] (zero outside the grid).
 enum LayerType { L_FIRST = 0, L_UP = 1, L_SAME = 2 };  // 1x1->kxk (s1,p0) | k4,s2,p1 | k3,s1,p1
 enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_Z = 3, EPI_STORE_F32 = 4,
-               EPI_DEN_LAYER = 5, EPI_DEN_FINAL = 6 };
+               EPI_DEN_LAYER = 5, EPI_DEN_FINAL = 6, EPI_STORE_F32_BIAS = 7 };  // 7: raw accumulators + bias[n] (fp32 rows)
 
 struct Tap { signed char plane, dy, dx, pad; };
 

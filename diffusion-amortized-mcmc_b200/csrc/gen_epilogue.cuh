@@ -80,6 +80,10 @@ __device__ __forceinline__ void epilogue_elem(const GemmPlan& p, int split, int 
     case EPI_STORE_F32: {
       reinterpret_cast<float*>(e.out)[(long long)m * e.nz_out + n] = acc;
     } break;
+    case EPI_STORE_F32_BIAS: {
+      reinterpret_cast<float*>(e.out)[(long long)m * e.nz_out + n] = acc + (e.bias ? e.bias[n] : 0.f);
+    } break;
+    default: break;
     case EPI_FWD_LAST: {
       const float xh = tanhf(acc + (e.bias ? e.bias[n] : 0.f));
       const int oy = y * e.sy + e.py, ox = x * e.sx + e.px;

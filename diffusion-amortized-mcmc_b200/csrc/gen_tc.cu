@@ -335,6 +335,17 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
                            __uint_as_float(raw[4 * q + 3]));
     return;
   }
+  if (e.kind == EPI_STORE_F32_BIAS && n0 + 16 <= p.N && e.bias != nullptr) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (long long)r.m * e.nz_out + n0);
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = __ldg(bp + q);
+      dst[q] = make_float4(__uint_as_float(raw[4 * q]) + bb.x, __uint_as_float(raw[4 * q + 1]) + bb.y,
+                           __uint_as_float(raw[4 * q + 2]) + bb.z, __uint_as_float(raw[4 * q + 3]) + bb.w);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int j = 0; j < 16; ++j)
     if (n0 + j < p.N) {

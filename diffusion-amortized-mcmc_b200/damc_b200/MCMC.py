@@ -383,6 +383,105 @@ def pack_denoiser(Q):
     return _cached(Q, "den", tensors, build)
 
 
+def _encoder_layers(enc):
+    """(conv, instnorm | None) pairs of an Encoder_* module: enc.net = Sequential(Conv2d, InstanceNorm2d, LeakyReLU, ...,
+    Conv2d)  (reference diffusion_net.py:233-263 / :274-310 / :321-369).  Raises if the stack has another shape."""
+    mods = list(enc.net)
+    pairs, i, slope = [], 0, None
+    while i < len(mods):
+        conv = mods[i]
+        if not isinstance(conv, nn.Conv2d):
+            raise RuntimeError(f"encoder.net[{i}]: expected Conv2d, found {type(conv).__name__}")
+        _no_hooks(conv, f"encoder.net[{i}]")
+        if conv.groups != 1 or conv.dilation != (1, 1) or conv.kernel_size[0] != conv.kernel_size[1] or \
+                conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.padding_mode != "zeros":
+            raise RuntimeError(f"encoder.net[{i}]: only square, ungrouped, undilated, zero-padded Conv2d is supported")
+        if i + 1 == len(mods):
+            pairs.append((conv, None))
+            break
+        norm, act = mods[i + 1], mods[i + 2] if i + 2 < len(mods) else None
+        if not isinstance(norm, nn.InstanceNorm2d) or not norm.affine or norm.track_running_stats:
+            raise RuntimeError(f"encoder.net[{i + 1}]: expected InstanceNorm2d(affine=True) without running statistics")
+        s = _slope_of(act, f"encoder.net[{i + 2}]")
+        if slope is not None and s != slope:
+            raise RuntimeError("encoder: all LeakyReLU slopes must be equal")
+        slope = s
+        pairs.append((conv, norm))
+        i += 3
+    return pairs, (slope if slope is not None else 0.2)
+
+
+def pack_encoder(enc, height, width, precision):
+    pairs, slope = _encoder_layers(enc)
+    eps = {float(n.eps) for _, n in pairs if n is not None}
+    if len(eps) > 1:
+        raise RuntimeError("encoder: InstanceNorm2d layers must share one eps")
+    params = [p for c, n in pairs for p in ([c.weight] + ([c.bias] if c.bias is not None else []) +
+                                            ([n.weight, n.bias] if n is not None else []))]
+
+    def build():
+        keep, arr = [], (_lib.ConvLayer * len(pairs))()
+
+        def ptr(t):
+            if t is None:
+                return None
+            c = _f32_cuda(t, "encoder parameter", True)
+            keep.append(c)
+            return c.data_ptr()
+
+        for i, (c, n) in enumerate(pairs):
+            arr[i] = _lib.ConvLayer(c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0],
+                                    ptr(c.weight), ptr(c.bias), ptr(n.weight if n is not None else None),
+                                    ptr(n.bias if n is not None else None))
+        out = C.c_void_p()
+        check(lib().damc_pack_encoder(C.byref(out), len(pairs), arr, int(height), int(width), slope,
+                                      eps.pop() if eps else 1e-5, _PRECISIONS[precision], _stream(keep[0].device)),
+              "damc_pack_encoder")
+        return _Handle(out), keep
+
+    return _cached(enc, f"enc_{precision}_{height}x{width}", params, build)
+
+
+def encoder_forward(enc, x, precision=None):
+    """xemb = enc(x) [B, nemb] through libdamc_b200: direct first convolution, k4-s2-p1 convolutions as the generator
+    engines' stride-2 GEMMs (tcgen05 for 'bf16' / 'fp16', CUDA-core for 'fp32'), fused InstanceNorm + LeakyReLU kernels.
+    Raises for encoders outside that family (e.g. the 28x28 MNIST encoder, odd-sized maps)."""
+    precision = precision or DEFAULT_DENOISER_PRECISION
+    xs = _f32_cuda(x, "x")
+    if xs.dim() != 4:
+        raise RuntimeError("x must be [B, nc, H, W]")
+    B, _, H, W = xs.shape
+    h = pack_encoder(enc, H, W, precision)
+    out = torch.empty(B, enc.nemb, dtype=torch.float32, device=xs.device)
+    nbytes = lib().damc_encoder_workspace_bytes(h.ptr, B)
+    ws = _workspace(xs.device, nbytes)
+    with torch.cuda.device(xs.device):
+        check(lib().damc_encoder_forward(h.ptr, C.c_void_p(xs.data_ptr()), C.c_void_p(out.data_ptr()), B,
+                                         C.c_void_p(ws.data_ptr()), nbytes, _stream(xs.device)), "damc_encoder_forward")
+    return out
+
+
+def _encoder_on_library(enc, x):
+    """True if Q.encoder is a stack damc_pack_encoder accepts for this image size (even maps down to the final k x k)."""
+    try:
+        pairs, _ = _encoder_layers(enc)
+    except (RuntimeError, AttributeError):
+        return False
+    H, W = x.shape[-2:]
+    for i, (c, n) in enumerate(pairs):
+        k, s, p = c.kernel_size[0], c.stride[0], c.padding[0]
+        if i == 0:
+            ok = (k, s, p) == (3, 1, 1) and c.in_channels <= 4 and c.out_channels % 64 == 0
+        elif i < len(pairs) - 1:
+            ok = (k, s, p) == (4, 2, 1) and H % 2 == 0 and W % 2 == 0 and c.in_channels % 64 == 0 and c.out_channels % 64 == 0
+            H, W = H // 2, W // 2
+        else:
+            ok = s == 1 and p == 0 and k == H == W and (k * k * c.in_channels) % 64 == 0 and c.out_channels % 16 == 0
+        if not ok:
+            return False
+    return len(pairs) >= 3
+
+
 def logsnr_table(T, logsnr_min, logsnr_max):
     """lambda(t_i), i = 0..T-1, evaluated in fp32 with the reference's formula (diffusion_helper_func.py:41-50,
     called at diffusion_net.py:599 with t = i/(T-1))."""
@@ -406,7 +505,12 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
         elif x is not None:
             assert b is None and device is None
             b, device = len(x), x.device
-            xemb = Q.encoder(x)
+            # tensor-core modes: the encoder runs on the library too (same operand precision as the denoiser GEMMs);
+            # the fp32 parity mode keeps torch's fp32 convolutions, as do encoders outside the supported family
+            if prec != _lib.PREC_FP32 and x.is_cuda and _encoder_on_library(Q.encoder, x):
+                xemb = encoder_forward(Q.encoder, x, precision or DEFAULT_DENOISER_PRECISION)
+            else:
+                xemb = Q.encoder(x)
         else:
             device = torch.device(device)
             xemb = Q.prior_emb(torch.randn(b, Q.nz, device=device))

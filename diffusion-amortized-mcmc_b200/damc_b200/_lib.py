@@ -15,6 +15,11 @@ class ConvTLayer(C.Structure):
                 ("weight", C.c_void_p), ("bias", C.c_void_p)]
 
 
+class ConvLayer(C.Structure):
+    _fields_ = [("cin", C.c_int), ("cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+                ("weight", C.c_void_p), ("bias", C.c_void_p), ("in_weight", C.c_void_p), ("in_bias", C.c_void_p)]
+
+
 class DenoiserDesc(C.Structure):
     _fields_ = [("nz", C.c_int), ("nxemb", C.c_int), ("ntemb", C.c_int), ("nf", C.c_int), ("residual", C.c_int),
                 ("time_w1", C.c_void_p), ("time_b1", C.c_void_p), ("time_w2", C.c_void_p), ("time_b2", C.c_void_p),
@@ -44,6 +49,9 @@ SIGNATURES = {
     "damc_denoise_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "damc_denoise": (_I, [_P, _P, _P, _I, _I, C.POINTER(_F), _I, _I, _P, _U64, _U64, _I, _P, _SZ, _P]),
     "damc_denoiser_eps": (_I, [_P, _P, _P, _F, _P, _I, _I, _P, _SZ, _P]),
+    "damc_pack_encoder": (_I, [C.POINTER(_P), _I, C.POINTER(ConvLayer), _I, _I, _F, _F, _I, _P]),
+    "damc_encoder_workspace_bytes": (_SZ, [_P, _I]),
+    "damc_encoder_forward": (_I, [_P, _P, _P, _I, _P, _SZ, _P]),
     "damc_launch_count": (C.c_longlong, []),
     "damc_profile_enable": (_I, [_I]),
     "damc_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -130,6 +130,26 @@ int damc_denoise(const damc_handle* den, float* z, const float* xemb, int B, int
 int damc_denoiser_eps(const damc_handle* den, const float* z, const float* xemb, float logsnr, float* eps_out, int B,
                       int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- image encoder of the amortizer  (replaces Q.encoder(x), reference src/diffusion_net.py:590 with Encoder_cifar10
+ *      :227-266 / Encoder_celeba64 :268-313 / Encoder_celebaHQ :315-372: Conv2d(nc,nif,3,1,1), Conv2d(.,.,4,2,1) x n,
+ *      Conv2d(.,nemb,k,1,0) on the final k x k map; InstanceNorm2d(affine) + LeakyReLU after every layer but the last).
+ *      The k4-s2-p1 layers run as the generator engines' stride-2 dgrad GEMMs (tcgen05 in the bf16/fp16 modes, CUDA-core
+ *      fp32 in DAMC_PREC_FP32).  Odd-sized maps (the 28x28 MNIST encoder) are not supported: hard error. ---------------- */
+typedef struct {
+  int cin, cout, k, stride, pad;
+  const float* weight;    /* Conv2d weight [cout,cin,k,k]                     */
+  const float* bias;      /* [cout] or NULL                                   */
+  const float* in_weight; /* InstanceNorm2d weight [cout]; NULL on the last layer */
+  const float* in_bias;   /* InstanceNorm2d bias   [cout]; NULL on the last layer */
+} damc_conv_layer;
+
+int damc_pack_encoder(damc_handle** out, int nlayers, const damc_conv_layer* host_layers, int height, int width,
+                      float negative_slope, float eps, int precision, void* stream);
+size_t damc_encoder_workspace_bytes(const damc_handle* enc, int B);
+/* xemb [B,nemb] = encoder(x [B,nc,H,W]) */
+int damc_encoder_forward(const damc_handle* enc, const float* x, float* xemb, int B, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------------------------
  * damc_launch_count : cumulative number of kernels this library has launched in the calling process.
  * damc_profile_enable(1) : bracket every generator GEMM launch with a cudaEvent pair on its own stream;

@@ -378,6 +378,56 @@ def test_damc_tensor_core_matches_fp32_kernel_on_ragged_batches(B, dev):
         assert torch.equal(one[0], outs["fp16"][0])
 
 
+ENC_TOL = {"fp32": 2e-4, "fp16": 5e-3, "bf16": 3e-2}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_encoder_against_reference_golden(prec, dev):
+    """Q.encoder(x) through libdamc_b200 (direct first conv, stride-2 convs as the dgrad GEMM plans, fused InstanceNorm +
+    LeakyReLU) against xemb produced by the UNMODIFIED reference Encoder_cifar10 (tests/golden/damc_cifar10_T100.npz)."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    g = np.load(os.path.join(GOLDEN, "damc_cifar10_T100.npz"), allow_pickle=True)
+    nz, nxemb, T, B = (int(v) for v in g["cfg"])
+    Q = dn._netQ_U(nc=3, nz=nz, nxemb=nxemb, ntemb=128, nif=64, diffusion_residual=True, n_interval=T,
+                   logsnr_min=-5.1, logsnr_max=9.8, var_type=str(g["var_type"]), with_noise=bool(g["with_noise"]),
+                   dataset="cifar10")
+    Q.load_state_dict(synth.module_state_like(Q, prefix="Q."))
+    Q = Q.to(dev).eval()
+    x = torch.tanh(synth.det_normal("x", (B, 3, 32, 32))).to(dev)
+    xemb = MCMC.encoder_forward(Q.encoder, x, precision=prec)
+    e = relmax(xemb, g["xemb"])
+    print(f"encoder[{prec}] vs reference golden: {e:.3e}")
+    assert e < ENC_TOL[prec], (prec, e)
+
+
+@pytest.mark.parametrize("dataset,H,B", [("cifar10", 32, 1), ("cifar10", 32, 37), ("celeba64", 64, 5), ("celebaHQ", 256, 3)])
+def test_encoder_families_match_torch(dataset, H, B, dev):
+    """Every supported encoder family and ragged batch sizes: the library's encoder against the same module run by torch
+    (fp32, TF32 off) on the GPU."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    enc = dn.Encoder(dataset, nc=3, nemb=256, nif=64)
+    enc.load_state_dict(synth.module_state_like(enc, prefix="enc."))
+    enc = enc.to(dev).eval()
+    x = torch.tanh(synth.det_normal("xe", (B, 3, H, H))).to(dev)
+    with torch.no_grad():
+        ref = enc(x)
+    for prec in ("fp32", "fp16", "bf16"):
+        out = MCMC.encoder_forward(enc, x, precision=prec)
+        e = relmax(out, ref)
+        print(f"{dataset} B={B} [{prec}]: {e:.3e}")
+        assert e < ENC_TOL[prec], (dataset, prec, e)
+
+
+def test_encoder_rejects_odd_sized_maps(dev):
+    """The 28x28 MNIST encoder halves 7x7 maps: no parity-plane layout -> hard error, and damc_sample keeps it in torch."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    enc = dn.Encoder("mnist", nc=1, nemb=128, nif=64).to(dev).eval()
+    x = torch.zeros(2, 1, 28, 28, device=dev)
+    assert not MCMC._encoder_on_library(enc, x)
+    with pytest.raises(RuntimeError):
+        MCMC.encoder_forward(enc, x, precision="bf16")
+
+
 def test_toy_amortizer_golden(dev):
     """_netQ_U_toy (reference toy_example/src/diffusion_net.py:141-239): nz = 2 latent, MLP encoder, T = 10."""
     from damc_b200 import MCMC, diffusion_net as dn

@@ -50,3 +50,15 @@ for B in sizes:
         out[f"B{B}_{prec}"] = {"ms": round(ms, 3), "reverse_steps_per_s": round(B * T / ms * 1e3)}
         print(f"B={B} {prec}: {ms:.3f} ms  {B * T / ms * 1e3 / 1e6:.2f} M reverse steps/s", flush=True)
 print(json.dumps(out))
+
+# whole Q(x) call (encoder + T reverse steps), torch encoder vs library encoder
+if os.environ.get("WITH_ENCODER", "1") == "1":
+    for B in sizes:
+        if B > 16384:
+            continue
+        x = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
+        with torch.no_grad():
+            ms_t = timed(lambda: Q.encoder(x))
+        ms_l = timed(lambda: MCMC.encoder_forward(Q.encoder, x, precision="fp16"))
+        ms_q = timed(lambda: MCMC.damc_sample(Q, x=x, seed=3, precision="fp16"))
+        print(f"B={B}: encoder torch {ms_t:.3f} ms, library fp16 {ms_l:.3f} ms; Q(x) fp16 end to end {ms_q:.3f} ms", flush=True)
