@@ -59,6 +59,8 @@ struct TcParams {
   uint32_t a_box_bytes, b_box_bytes, idesc;
   int wm_shift, per_img_shift;  // log2(Wm), log2(Ht*Wm) when powers of two, else -1 (row decode without divisions)
   int cls_inner;    // merged parity classes: class index is the fastest tile dimension
+  int direct;       // staged-epilogue launches: lanes store their own row pieces with 256-bit stores, no smem staging tiles
+  int dbg;          // experiment switches (env DAMC_TC_DBG): 1 = skip the staged epilogue's global stores, 2 = skip its math
   int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
 };
 
@@ -364,7 +366,8 @@ struct StagedEpi {
   static constexpr uint32_t row_bytes = SW * 2;
   unsigned long long out_bits;
   unsigned long long mrow_bits;  // this lane's row of mask words (1 bit per element), or 0
-  int sub, j;
+  int sub, j, dbg;
+  int direct;  // 1: each lane stores its own row piece with 256-bit stores (no smem round trip); 0: staged through smem
 
   __device__ __forceinline__ static unsigned long long act_ptr_bits(const GemmPlan& p, const RowCtx& rc) {
     return (unsigned long long)(reinterpret_cast<const __nv_bfloat16*>(p.epi.act) + (rc.ok ? (long long)rc.m * p.N : 0ll));
@@ -428,6 +431,7 @@ struct StagedEpi {
     const bool is_mask = e.kind == EPI_DGRAD_MASK;
     const bool bits = e.maskbits != nullptr;
     uint32_t wout[2] = {0u, 0u};
+    if (dbg & 2) return;
 #pragma unroll 1
     for (int c = 0; c < SW; c += 32) {
       uint32_t v[32];
@@ -435,6 +439,7 @@ struct StagedEpi {
       tmem_ld_wait();
       const uint32_t mword = c == 0 ? mw.x : mw.y;
       uint32_t oword = 0u;
+      uint32_t wprev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int jj = (c >> 3) + g;
@@ -471,12 +476,26 @@ struct StagedEpi {
             w[t2] = pack2(p.op_fp16, h0, h1);
           }
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        if (direct) {
+          // 8 columns = 16 bytes of this lane's own row; two g's make one 256-bit store (full 32-byte sectors)
+          if (g & 1) {
+            if (out_bits && !(dbg & 1)) {
+              const unsigned long long a = out_bits + 2ull * (unsigned long long)(n_base + c + 8 * (g - 1));
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(wprev[0]), "r"(wprev[1]),
+                           "r"(wprev[2]), "r"(wprev[3]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
+          } else {
+            wprev[0] = w[0]; wprev[1] = w[1]; wprev[2] = w[2]; wprev[3] = w[3];
+          }
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
       }
       wout[c >> 5] = oword;
     }
     if (!is_mask && bits && mrow_bits)  // sign bits of this row's 64 pre-activations (consumed by the dgrad epilogue)
       *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(mrow_bits) + (n_base >> 5)) = make_uint2(wout[0], wout[1]);
+    if (direct) return;
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {  // write-out: 8 consecutive lanes cover one contiguous 128-byte row piece
@@ -485,7 +504,7 @@ struct StagedEpi {
       const uint32_t src = my_stage + (uint32_t)R * row_bytes + (uint32_t)((j ^ (R & (CPR - 1))) << 4);
       uint4 o4;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "r"(src) : "memory");
-      if (pb) *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pb) + n_base) + j) = o4;
+      if (pb && !(dbg & 1)) *(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pb) + n_base) + j) = o4;
     }
     __syncwarp();
   }
@@ -580,12 +599,14 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = unit; tile < total_tiles; tile += nunits) {
-        int mt, nt, sp, b0, y0;
-        decode(tile, mt, nt, sp);
+    // lane 0 issues the loads.  (Tried and dropped: idle lanes prefetching the next tile's A window into L2 with
+    // cp.async.bulk.prefetch.tensor -- 3-7 % slower on the MMA-bound launches.)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = unit; lane == 0 && tile < total_tiles; tile += nunits) {
+      int mt, nt, sp, b0, y0;
+      decode(tile, mt, nt, sp);
+      {
         tile_origin(mt, b0, y0);
         const int cls = ncls > 1 ? sp : 0;
         const int kb0 = ncls > 1 ? 0 : sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
@@ -682,6 +703,8 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       };
       const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (32u * 128u);
       StagedEpi se;
+      se.dbg = P.dbg;
+      se.direct = P.direct;
       se.sub = lane / StagedEpi::CPR;
       se.j = lane % StagedEpi::CPR;
       if (nseg_w == 0) {
@@ -934,6 +957,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
   P.stage_cols = 0;
   P.cls_inner = getenv("DAMC_TC_CLS_OUTER") ? 0 : 1;
+  P.dbg = getenv("DAMC_TC_DBG") ? atoi(getenv("DAMC_TC_DBG")) : 0;
   if ((p.epi.kind == EPI_FWD_ACT || p.epi.kind == EPI_DGRAD_MASK) && !getenv("DAMC_TC_NOSTAGE")) {
     if (P.BN % 64 == 0 && p.N % 64 == 0 && (p.epi.kind != EPI_FWD_ACT || p.epi.bias_mod % 64 == 0)) P.stage_cols = 64;
   }
@@ -956,13 +980,17 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.fd_bias = make_fastdiv(1);
   if (den_kind) { P.bias_src = p.epi.den.bias4; P.bias_floats = p.Np; P.bias_off = ew * 2048; }
   else if (P.stage_cols && p.epi.kind == EPI_FWD_ACT) {
-    P.bias_src = p.epi.bias; P.bias_floats = p.epi.bias_mod; P.bias_off = ew * TC_STAGING_PER_WARP;
+    P.bias_src = p.epi.bias; P.bias_floats = p.epi.bias_mod; P.bias_off = -1;  // set below: right behind the staging tiles
     P.fd_bias = make_fastdiv(p.epi.bias_mod);
   }
-  const int tiles_bytes = P.stage_cols ? ew * TC_STAGING_PER_WARP : den_kind ? ew * 2048 : 0;
+  // the sign-from-activations dgrad variant (DAMC_TC_NOBITS) stashes activation rows in the staging tiles; every other
+  // staged launch writes its rows directly from registers and needs no tiles
+  P.direct = (P.stage_cols && !(P.dbg & 4) && !(p.epi.kind == EPI_DGRAD_MASK && p.epi.maskbits == nullptr)) ? 1 : 0;
+  const int tiles_bytes = P.stage_cols ? (P.direct ? 0 : ew * TC_STAGING_PER_WARP) : den_kind ? ew * 2048 : 0;
   auto stages_for = [&](int sb) { return std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - sb) / stage_bytes)); };
   if (!den_kind && stages_for(tiles_bytes + P.bias_floats * 4 + 128) < stages_for(tiles_bytes + 128))
     P.bias_floats = 0;  // a pipeline stage is worth more than the smem bias: the epilogue reads the bias through L1 instead
+  if (P.bias_off < 0) P.bias_off = tiles_bytes;
   const int staging_bytes = tiles_bytes + P.bias_floats * 4 + 128;
   P.stages = stages_for(staging_bytes);
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
