@@ -118,7 +118,7 @@ __device__ __forceinline__ uint16_t den_cvt(bool fp16, float v) {
 //                           feeds 8 FMAs; phase, sin and cos in fp32                                (diffusion_net.py:497-499)
 //   blocks [nb_embed, ..) : ctx activations c_L = SiLU(cx + ct) of CTX_CHAINS chains, float4 in / 4 x 16-bit out, written into
 //                           the [din, din+dout) slice of each layer's operand rows                  (:426-433, hoisted halves)
-constexpr int EMB_CHAINS = 32, CTX_CHAINS = 8;
+constexpr int EMB_CHAINS = 32, EMB_PITCH = 36, CTX_CHAINS = 8;  // pitch 36: 16-byte aligned rows, 4-way (not 32-way) conflicts on the transposing store
 __global__ void __launch_bounds__(256) den_prep_kernel(const DenPrepArgs a, int nb_embed) {
   extern __shared__ __align__(16) float sm[];
   const int nz = a.nz, half = nz >> 1;
@@ -129,25 +129,28 @@ __global__ void __launch_bounds__(256) den_prep_kernel(const DenPrepArgs a, int 
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((int)blockIdx.x < nb_embed) {
     float* Bs = sm;               // [nz][half]
-    float* zs = sm + nz * half;   // [EMB_CHAINS][nz]
+    float* zs = sm + nz * half;   // [nz][EMB_PITCH]  (transposed: the 8 chains of a thread are two float4 reads)
     const int b0 = blockIdx.x * EMB_CHAINS;
     const int nb = min(EMB_CHAINS, a.B - b0);
     for (int i = threadIdx.x; i < nz * half / 4; i += blockDim.x)
       reinterpret_cast<float4*>(Bs)[i] = __ldg(reinterpret_cast<const float4*>(a.Bp) + i);
-    for (int i = threadIdx.x; i < EMB_CHAINS * nz / 4; i += blockDim.x)
-      reinterpret_cast<float4*>(zs)[i] = i < nb * nz / 4 ? *(reinterpret_cast<const float4*>(a.z + (size_t)b0 * nz) + i)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < EMB_CHAINS * nz; i += blockDim.x) {
+      const int c = i / nz, k = i - c * nz;   // coalesced over k
+      zs[k * EMB_PITCH + c] = c < nb ? a.z[(size_t)(b0 + c) * nz + k] : 0.f;
+    }
     __syncthreads();
     uint16_t* A0 = reinterpret_cast<uint16_t*>(a.A[0]);
     for (int i = threadIdx.x; i < (EMB_CHAINS / 8) * half; i += blockDim.x) {
       const int cg = i / half, j = i - cg * half;
-      const float* zr = zs + cg * 8 * nz;
+      const float* zr = zs + cg * 8;
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
       for (int k = 0; k < nz; ++k) {
         const float w = Bs[k * half + j];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(zr[c * nz + k], w, acc[c]);
+        const float4 z0 = *reinterpret_cast<const float4*>(zr + k * EMB_PITCH);
+        const float4 z1 = *reinterpret_cast<const float4*>(zr + k * EMB_PITCH + 4);
+        acc[0] = fmaf(z0.x, w, acc[0]); acc[1] = fmaf(z0.y, w, acc[1]); acc[2] = fmaf(z0.z, w, acc[2]); acc[3] = fmaf(z0.w, w, acc[3]);
+        acc[4] = fmaf(z1.x, w, acc[4]); acc[5] = fmaf(z1.y, w, acc[5]); acc[6] = fmaf(z1.z, w, acc[6]); acc[7] = fmaf(z1.w, w, acc[7]);
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -161,29 +164,36 @@ __global__ void __launch_bounds__(256) den_prep_kernel(const DenPrepArgs a, int 
         }
       }
     }
-    for (int i = threadIdx.x; i < nb * nz / 4; i += blockDim.x) {  // the raw z slice
-      const int c = i / (nz / 4), k4 = i - c * (nz / 4);
-      const float4 v = reinterpret_cast<const float4*>(zs)[i];
-      const uint2 o = make_uint2((uint32_t)den_cvt(fp16, v.x) | ((uint32_t)den_cvt(fp16, v.y) << 16),
-                                 (uint32_t)den_cvt(fp16, v.z) | ((uint32_t)den_cvt(fp16, v.w) << 16));
-      *reinterpret_cast<uint2*>(A0 + (size_t)(b0 + c) * a.ld[0] + 2 * half + 4 * k4) = o;
+    for (int i = threadIdx.x; i < nb * (nz / 2); i += blockDim.x) {  // the raw z slice, two elements per thread
+      const int c = i / (nz / 2), k2 = (i - c * (nz / 2)) * 2;
+      const uint32_t o = (uint32_t)den_cvt(fp16, zs[k2 * EMB_PITCH + c]) | ((uint32_t)den_cvt(fp16, zs[(k2 + 1) * EMB_PITCH + c]) << 16);
+      *reinterpret_cast<uint32_t*>(A0 + (size_t)(b0 + c) * a.ld[0] + 2 * half + k2) = o;
     }
     return;
   }
   const int b0 = ((int)blockIdx.x - nb_embed) * CTX_CHAINS;
   const int nb = min(CTX_CHAINS, a.B - b0);
   const int g4 = a.csum >> 2;
-  for (int i = threadIdx.x; i < nb * g4; i += blockDim.x) {
-    const int c = i / g4, col = (i - c * g4) << 2;
+  for (int g = threadIdx.x; g < g4; g += blockDim.x) {   // this thread's 4 ctx columns: same layer / offset for every chain
+    const int col = g << 2;
     int L = 0;
 #pragma unroll
     for (int l = 1; l < DEN_LAYERS; ++l) L += col >= a.coff[l];
-    const float4 x4 = *reinterpret_cast<const float4*>(a.cx + (size_t)(b0 + c) * a.csum + col);
     const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.ctrow + col));
-    const uint2 o = make_uint2(
-        (uint32_t)den_cvt(fp16, den_silu(x4.x + t4.x)) | ((uint32_t)den_cvt(fp16, den_silu(x4.y + t4.y)) << 16),
-        (uint32_t)den_cvt(fp16, den_silu(x4.z + t4.z)) | ((uint32_t)den_cvt(fp16, den_silu(x4.w + t4.w)) << 16));
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.A[L]) + (size_t)(b0 + c) * a.ld[L] + a.din[L] + (col - a.coff[L])) = o;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(a.A[L]) + a.din[L] + (col - a.coff[L]);
+    const int ld = a.ld[L];
+    float4 x4[CTX_CHAINS];
+#pragma unroll
+    for (int c = 0; c < CTX_CHAINS; ++c)   // all loads in flight before the first use
+      x4[c] = c < nb ? *reinterpret_cast<const float4*>(a.cx + (size_t)(b0 + c) * a.csum + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < CTX_CHAINS; ++c) {
+      if (c >= nb) break;
+      const uint2 o = make_uint2(
+          (uint32_t)den_cvt(fp16, den_silu(x4[c].x + t4.x)) | ((uint32_t)den_cvt(fp16, den_silu(x4[c].y + t4.y)) << 16),
+          (uint32_t)den_cvt(fp16, den_silu(x4[c].z + t4.z)) | ((uint32_t)den_cvt(fp16, den_silu(x4[c].w + t4.w)) << 16));
+      *reinterpret_cast<uint2*>(dst + (size_t)(b0 + c) * ld) = o;
+    }
   }
 }
 
@@ -228,7 +238,7 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
   for (int i = 0; i < DEN_LAYERS; ++i) {
     pa.A[i] = w.A[i]; pa.ld[i] = d->din[i] + d->dout[i]; pa.din[i] = d->din[i]; pa.dout[i] = d->dout[i]; pa.coff[i] = d->coff[i];
   }
-  const size_t prep_smem = sizeof(float) * ((size_t)d->nz * (d->nz / 2) + (size_t)EMB_CHAINS * d->nz);
+  const size_t prep_smem = sizeof(float) * ((size_t)d->nz * (d->nz / 2) + (size_t)EMB_PITCH * d->nz);
   DAMC_CUDA(cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
   const int nb_embed = ceil_div(B, EMB_CHAINS), nb_ctx = ceil_div(B, CTX_CHAINS);
   for (int st = 0; st < nsteps; ++st) {

@@ -92,6 +92,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 27)) __trap();
 }
+// Long waits of many warps (the epilogue warps wait most of a tile's main loop for its accumulator): back off with
+// nanosleep after a few polls so that spinning warps stop burning issue slots and power -- the step is power-capped.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > 4) __nanosleep(spin > 64 ? 512 : 128);
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -709,7 +717,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       se.j = lane % StagedEpi::CPR;
       if (nseg_w == 0) {
         for (int k = 0; k < ntl; ++k) {
-          mbar_wait(bar_tfull(k & 1), (uint32_t)(k >> 1) & 1u);
+          mbar_wait_relaxed(bar_tfull(k & 1), (uint32_t)(k >> 1) & 1u);
           __syncwarp();
           if (lane == 0) release_acc(k & 1);
         }
@@ -751,7 +759,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             advance(nxt);
           }
           if (sg == 0) {
-            mbar_wait(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
+            mbar_wait_relaxed(bar_tfull(as), (uint32_t)(k >> 1) & 1u);
             tc_fence_after();
           }
           if (n_base < p.N) {
@@ -787,7 +795,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int nt, sp;
         const RowCtx rc = row_ctx(tile, nt, sp);
         const int as = it & 1;
-        mbar_wait(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
+        mbar_wait_relaxed(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_row = t_lane + (uint32_t)as * 256u + (uint32_t)(grp * cols_w);
         const int n_w = nt * P.BN + grp * cols_w;  // first accumulator column of this warp
@@ -846,7 +854,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int nt, sp;
         const RowCtx rc = row_ctx(tile, nt, sp);
         const int as = it & 1;
-        mbar_wait(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
+        mbar_wait_relaxed(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_row = t_lane + (uint32_t)as * 256u;
         for (int c = grp * 32; c < P.BN; c += 32 * NG) {

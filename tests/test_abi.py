@@ -81,3 +81,19 @@ def test_state_dict_keys_match_reference_layout():
               "xemb", "prior_emb.2.weight"):
         assert k in keys, k
     assert sum(p.numel() for p in Q.p.parameters()) == 3143424
+
+
+def test_encoder_family_detection(built_lib):
+    """Host-side structure check that decides whether Q.encoder runs on the library (even-sized maps down to the final
+    k x k) or stays in torch (the 28x28 MNIST encoder)."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    assert MCMC._encoder_on_library(dn.Encoder("cifar10", nc=3, nemb=1024, nif=64), torch.zeros(1, 3, 32, 32))
+    assert MCMC._encoder_on_library(dn.Encoder("celeba64", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 64, 64))
+    assert MCMC._encoder_on_library(dn.Encoder("celebaHQ", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 256, 256))
+    assert not MCMC._encoder_on_library(dn.Encoder("mnist", nc=1, nemb=128, nif=64), torch.zeros(1, 1, 28, 28))
+    assert not MCMC._encoder_on_library(dn.Encoder("cifar10", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 48, 48))
+    enc = dn.Encoder("cifar10", nc=3, nemb=128, nif=64)
+    enc.net[1] = torch.nn.BatchNorm2d(64)
+    assert not MCMC._encoder_on_library(enc, torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MCMC.encoder_forward(dn.Encoder("cifar10", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 32, 32), precision="bf16")

@@ -41,9 +41,13 @@ Q = dn._netQ_U(nc=3, nz=128, nxemb=1024, ntemb=128, nif=64, diffusion_residual=T
 for B in (128, 4096):
     x = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
     with torch.no_grad():
-        ms = timed(lambda: Q(x), reps=3)
         ms_enc = timed(lambda: Q.encoder(x), reps=3)
-    out[f"damc_B{B}_T100"] = {"ms": ms, "encoder_ms": ms_enc, "reverse_steps_per_s": B * 100 / ms * 1e3}
+        out[f"damc_B{B}_T100_torch_encoder"] = {"ms": ms_enc}
+        for prec in ("fp32", "fp16", "bf16"):  # fp32: persistent CUDA-core kernel + torch encoder; fp16/bf16: tcgen05 + library encoder
+            ms = timed(lambda: Q(x, precision=prec), reps=3)
+            out[f"damc_B{B}_T100_{prec}"] = {"ms": ms, "reverse_steps_per_s": B * 100 / ms * 1e3}
+        ms_p = timed(lambda: Q(x=None, b=B, device=dev, precision="fp16"), reps=3)
+        out[f"damc_prior_B{B}_T100_fp16"] = {"ms": ms_p, "reverse_steps_per_s": B * 100 / ms_p * 1e3}
 # posterior at the reference's training batch (B = 128), fp32 and bf16
 _, x = bench.make_inputs(G, 128, dev, 3)
 z0 = torch.randn(128, 128, device=dev)
