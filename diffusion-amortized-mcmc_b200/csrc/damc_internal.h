@@ -42,10 +42,14 @@ enum EpiKind { EPI_FWD_ACT = 0, EPI_FWD_LAST = 1, EPI_DGRAD_MASK = 2, EPI_DGRAD_
 
 struct Tap { signed char plane, dy, dx, pad; };
 
-// DAMC denoiser layer on the tcgen05 engine: the GEMM's columns come in quads (gate, hyper-bias, main, skip) per output
-// feature n; the epilogue forms out = (main+b) sigmoid(gate+bg) + hb + skip + bs  (reference diffusion_net.py:439-445).
+// DAMC denoiser layer on the tcgen05 engine: every N tile of BN columns holds the four terms of BN/4 output features as
+// column blocks [gate | hyper-bias | main | skip]; the K axis is [layer input h (din) | ctx activation c (dout)], and an
+// h k-block feeds only (main, skip), a c k-block only (gate, hyper-bias) -- half-width MMAs, no structural zeros.  The
+// epilogue forms out = (main+b) sigmoid(gate+bg) + hb + skip + bs  (reference diffusion_net.py:439-445).
 struct DenEpi {
-  const float* bias4;          // [4*dout] interleaved (bg, 0, b, bs)
+  int din;                     // width of the h part of the K axis (multiple of 64)
+  int bn;                      // N tile width the weight rows were packed for (256 | 128 | 64); must match the launch
+  const float* bias4;          // [4*dout] per feature (bg, 0, b, bs)
   void* dst1; int ld1, off1;   // leaky_relu(out, .01) -> dst1[b*ld1 + off1 + n]   (operand type)
   void* dst2; int ld2, off2;   // second destination (U-net skip), or null
   // EPI_DEN_FINAL: eps = z + out ; reverse update of z (reference diffusion_net.py:610-620)
@@ -152,6 +156,7 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream);
 // prepared launches (tensor maps encoded once, replayed many times; the plan's epilogue scalars stay editable)
 struct TcLaunch;
 int tc_prepare(const GemmPlan& p, int precision, TcLaunch** out);
+int tc_den_tile_width(int B, int Np);   // N tile width convgemm will use for a denoiser layer with Np = 4*dout columns
 GemmPlan* tc_plan(TcLaunch* l);
 int tc_launch(TcLaunch* l, cudaStream_t stream);
 void tc_free(TcLaunch* l);
@@ -178,12 +183,14 @@ constexpr int DEN_TM = 16;        // chains per CTA (fp32 streaming kernel)
 constexpr int DEN_THREADS = 256;  // = max dout
 constexpr int DEN_MAXW = 512;     // widest layer input (concat of two 64*nf halves)
 
-// tcgen05 operands of one precision (bf16 | fp16): per layer one K-major weight matrix whose rows come in quads
-// (gate, hyper-bias, main, skip) per output feature and whose K axis is [layer input (din) | ctx activation (dout)].
+// tcgen05 operands of one precision (bf16 | fp16): per layer one K-major weight matrix [4*dout][din+dout] whose rows are
+// grouped per N tile as [gate | hyper-bias | main | skip] blocks of BN/4 features; one copy per tile width in use.
+constexpr int DEN_NBN = 3;   // tile widths 256, 128, 64
 struct DenTcPack {
   void* slab = nullptr;
-  void* Wq[DEN_LAYERS];      // [4*dout][din+dout]  operand type
-  float* bias4[DEN_LAYERS];  // [4*dout]            (bg, 0, b, bs)
+  void* Wq[DEN_NBN][DEN_LAYERS];  // [bn index][layer]: [4*dout][din+dout] operand type
+  bool live[DEN_NBN] = {false, false, false};   // packed (and kept fresh by refill) once a launch has asked for it
+  float* bias4[DEN_LAYERS];       // [4*dout] (bg, 0, b, bs)
 };
 
 struct DenPack : damc_handle {

@@ -7,8 +7,9 @@
 //     O(10) radians, so it is formed in fp32 and only the result is rounded to the operand type) and the ctx activations
 //     c_L = SiLU(cx + ct[t]) of all 7 layers, written straight into the layers' operand rows;
 //   * one convgemm_tc_kernel launch per ConcatSquashLinearSkipCtx layer.  The four Linears of a layer become ONE GEMM:
-//     operand row = [h (din) | c_L (dout)], weight rows in quads (gate, hyper-bias, main, skip) per output feature, so a
-//     thread's 16 accumulator columns hold the four terms of 4 features and the epilogue forms
+//     operand row = [h (din) | c_L (dout)]; every N tile holds the four terms of BN/4 output features as column blocks
+//     [gate | hyper-bias | main | skip].  An h k-block multiplies only the (main, skip) weight rows, a c k-block only the
+//     (gate, hyper-bias) rows (half-width MMAs into the matching half of the TMEM accumulator), and the epilogue forms
 //         out = (main + b) * sigmoid(gate + bg) + hyper_bias + skip + bs                             (:439-445)
 //     writes leaky_relu(out, 0.01) as the next layer's operand (and the U-net skip copy), or -- last layer -- applies
 //     eps = z + out and the reverse update of z (:610-620) in fp32.
@@ -23,16 +24,17 @@
 
 namespace damc {
 
-// ---- packing: [4*dout][din+dout] quad rows ---------------------------------------------------------------------------
+// ---- packing: [4*dout][din+dout]; rows of N tile t (bn rows): [gate Q | hyper-bias Q | main Q | skip Q], Q = bn/4 -------
 template <typename T>
-__global__ void pack_den_quad(const float* __restrict__ W, const float* __restrict__ Ws, const float* __restrict__ Wg,
-                              const float* __restrict__ Wb, int din, int dout, T* __restrict__ dst) {
-  const int Kt = din + dout;
+__global__ void pack_den_blocks(const float* __restrict__ W, const float* __restrict__ Ws, const float* __restrict__ Wg,
+                                const float* __restrict__ Wb, int din, int dout, int bn, T* __restrict__ dst) {
+  const int Kt = din + dout, Q = bn >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4ll * dout * Kt) return;
   const int row = (int)(i / Kt), k = (int)(i - (long long)row * Kt);
-  const int n = row >> 2, q = row & 3;
-  float v = 0.f;
+  const int tile = row / bn, r = row - tile * bn;
+  const int q = r / Q, n = tile * Q + (r - q * Q);   // q: 0 gate, 1 hyper-bias, 2 main, 3 skip ; n: output feature
+  float v = 0.f;   // the (gate, hyper-bias) x h and (main, skip) x c blocks are never loaded; keep them zero anyway
   if (q == 0) { if (k >= din) v = Wg[(size_t)n * dout + (k - din)]; }
   else if (q == 1) { if (k >= din) v = Wb[(size_t)n * dout + (k - din)]; }
   else if (q == 2) { if (k < din) v = W[(size_t)n * din + k]; }
@@ -52,20 +54,33 @@ void den_tc_free(DenTcPack* t) {
   delete t;
 }
 
-int den_tc_refill(const DenPack* d, int precision, cudaStream_t s) {
+static const int kDenBn[DEN_NBN] = {256, 128, 64};
+static int den_bn_index(int bn) { return bn == 256 ? 0 : bn == 128 ? 1 : 2; }
+
+static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStream_t s) {
   DenTcPack* t = d->tc[precision];
-  if (!t) return DAMC_OK;
   const damc_denoiser_desc* h = &d->src;
   for (int i = 0; i < DEN_LAYERS; ++i) {
     const int di = d->din[i], dn = d->dout[i];
     const long long n = 4ll * dn * (di + dn);
     const int blocks = (int)((n + 255) / 256);
     if (precision == DAMC_PREC_FP16)
-      pack_den_quad<__half><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, (__half*)t->Wq[i]);
+      pack_den_blocks<__half><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__half*)t->Wq[v][i]);
     else
-      pack_den_quad<__nv_bfloat16><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, (__nv_bfloat16*)t->Wq[i]);
-    pack_den_bias4<<<ceil_div(dn, 128), 128, 0, s>>>(h->b[i], h->bs[i], h->bg[i], dn, t->bias4[i]);
+      pack_den_blocks<__nv_bfloat16><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__nv_bfloat16*)t->Wq[v][i]);
   }
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+int den_tc_refill(const DenPack* d, int precision, cudaStream_t s) {
+  DenTcPack* t = d->tc[precision];
+  if (!t) return DAMC_OK;
+  const damc_denoiser_desc* h = &d->src;
+  for (int v = 0; v < DEN_NBN; ++v)
+    if (t->live[v]) DAMC_TRY(den_tc_pack_variant(d, precision, v, s));
+  for (int i = 0; i < DEN_LAYERS; ++i)
+    pack_den_bias4<<<ceil_div(d->dout[i], 128), 128, 0, s>>>(h->b[i], h->bs[i], h->bg[i], d->dout[i], t->bias4[i]);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
@@ -75,19 +90,23 @@ int den_tc_ensure(const DenPack* d, int precision, cudaStream_t s) {
   if (d->tc[precision]) return DAMC_OK;
   if (!tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "denoiser: the tcgen05 engine needs cuTensorMapEncodeTiled from the driver");
   if (d->nz % 4) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "denoiser (tensor-core mode): nz %d must be a multiple of 4", d->nz);
-  size_t bytes = 0;
+  size_t wbytes = 0, bbytes = 0;
   for (int i = 0; i < DEN_LAYERS; ++i) {
     if (d->din[i] % 64 || d->dout[i] % 64)
       DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "denoiser (tensor-core mode): layer %d widths %d -> %d must be multiples of 64; use precision fp32",
                 i, d->din[i], d->dout[i]);
-    bytes += align_up(2 * 4 * (size_t)d->dout[i] * (d->din[i] + d->dout[i]), 256) + align_up(16 * (size_t)d->dout[i], 256);
+    wbytes += align_up(2 * 4 * (size_t)d->dout[i] * (d->din[i] + d->dout[i]), 256);
+    bbytes += align_up(16 * (size_t)d->dout[i], 256);
   }
   DenTcPack* t = new DenTcPack();
-  if (cudaMalloc(&t->slab, bytes) != cudaSuccess) { delete t; DAMC_FAIL(DAMC_ERR_CUDA, "denoiser: cudaMalloc(%zu) failed", bytes); }
+  if (cudaMalloc(&t->slab, DEN_NBN * wbytes + bbytes) != cudaSuccess) { delete t; DAMC_FAIL(DAMC_ERR_CUDA, "denoiser: cudaMalloc(%zu) failed", DEN_NBN * wbytes + bbytes); }
   char* p = (char*)t->slab;
+  for (int v = 0; v < DEN_NBN; ++v)
+    for (int i = 0; i < DEN_LAYERS; ++i) {
+      t->Wq[v][i] = p;
+      p += align_up(2 * 4 * (size_t)d->dout[i] * (d->din[i] + d->dout[i]), 256);
+    }
   for (int i = 0; i < DEN_LAYERS; ++i) {
-    t->Wq[i] = p;
-    p += align_up(2 * 4 * (size_t)d->dout[i] * (d->din[i] + d->dout[i]), 256);
     t->bias4[i] = (float*)p;
     p += align_up(16 * (size_t)d->dout[i], 256);
   }
@@ -214,11 +233,18 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
     p.B = B; p.Hm = 1; p.Wm = 1; p.Cs = d->din[i] + d->dout[i];
     p.ntaps = 1;
     p.taps[0] = Tap{0, 0, 0, 0};
-    p.Wtc = t->Wq[i];
     p.N = p.Np = 4 * d->dout[i];
+    const int bn = tc_den_tile_width(B, p.Np), v = den_bn_index(bn);
+    if (!t->live[v]) {   // first launch with this tile width: pack that row order now, refill() keeps it fresh afterwards
+      d->tc[precision]->live[v] = true;
+      DAMC_TRY(den_tc_pack_variant(d, precision, v, s));
+    }
+    p.Wtc = t->Wq[v][i];
     p.ksplit = 1;
     p.epi.kind = i == DEN_LAYERS - 1 ? EPI_DEN_FINAL : EPI_DEN_LAYER;
     DenEpi& e = p.epi.den;
+    e.din = d->din[i];
+    e.bn = bn;
     e.bias4 = t->bias4[i];
     if (i < DEN_LAYERS - 1) {
       e.dst1 = w.A[i + 1]; e.ld1 = d->din[i + 1] + d->dout[i + 1]; e.off1 = 0;

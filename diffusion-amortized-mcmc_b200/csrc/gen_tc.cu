@@ -59,6 +59,7 @@ struct TcParams {
   uint32_t a_box_bytes, b_box_bytes, idesc;
   int wm_shift, per_img_shift;  // log2(Wm), log2(Ht*Wm) when powers of two, else -1 (row decode without divisions)
   int cls_inner;    // merged parity classes: class index is the fastest tile dimension
+  int den_kb_h;     // denoiser launches: k-blocks [0, den_kb_h) carry the layer input h, the rest the ctx activation c
   int direct;       // staged-epilogue launches: lanes store their own row pieces with 256-bit stores, no smem staging tiles
   int dbg;          // experiment switches (env DAMC_TC_DBG): 1 = skip the staged epilogue's global stores, 2 = skip its math
   int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
@@ -242,14 +243,8 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ uint32_t pack2(bool fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
 
 // ---- DAMC denoiser epilogues (EPI_DEN_LAYER / EPI_DEN_FINAL) ------------------------------------------------------------
-// Accumulator columns come in quads (gate, hyper-bias, main, skip) per output feature; sb = this launch's bias quads
-// (bg, 0, b, bs) in shared memory.   out = (main + b) * sigmoid(gate + bg) + hyper_bias + skip + bs   (diffusion_net.py:439-445)
-__device__ __forceinline__ float den_out(const uint32_t* raw4, const float* sb4) {
-  const float4 bq = *reinterpret_cast<const float4*>(sb4);
-  const float gate = __uint_as_float(raw4[0]) + bq.x, hb = __uint_as_float(raw4[1]);
-  const float mainv = __uint_as_float(raw4[2]) + bq.z, skip = __uint_as_float(raw4[3]) + bq.w;
-  return fmaf(mainv, __fdividef(1.f, 1.f + __expf(-gate)), hb + skip);
-}
+// out = (main + b) * sigmoid(gate + bg) + hyper_bias + skip + bs   (diffusion_net.py:439-445), formed in the kernel's
+// denoiser branch from the four column blocks of the accumulator; bias quads (bg, 0, b, bs) per feature sit in smem.
 // last layer, 4 features [f0, f0+4) of chain r.b:  eps = z + out (residual, :530-531); x0 prediction and ancestral update
 // of z (:610-620), fp32 throughout
 __device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, const float outv[4]) {
@@ -571,12 +566,14 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const bool den_kind = P.plan.epi.kind == EPI_DEN_LAYER || P.plan.epi.kind == EPI_DEN_FINAL;
   // the launch's bias vector (forward: [Cout]; denoiser: bias quads of the whole layer) lives in smem behind the staging tiles
   float* den_bias = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) + P.bias_off);
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
+  // The bias vector is written by the handle's refill kernels, which precede a non-PDL kernel of the same call (stage_z /
+  // the hoist kernels), so it is complete before any PDL-launched kernel of the chain can start: safe to read early.
   for (int i = threadIdx.x; i < P.bias_floats; i += blockDim.x) den_bias[i] = __ldg(P.bias_src + i);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
   tc_fence_after();
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const GemmPlan& p = P.plan;
@@ -633,7 +630,10 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           } else {
             mbar_expect_tx(bar_full(stage), P.a_box_bytes + P.b_box_bytes);
             tma_load_5d(sa, &tmA, bar_full(stage), c0, (int)tp.dx, y0 + (int)tp.dy, b0, (int)tp.plane);
-            tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, wrow0 + t * p.Np + nt * P.BN);
+            // denoiser tiles hold [gate | hyper-bias | main | skip] column blocks: an h k-block only feeds (main, skip),
+            // a c k-block only (gate, hyper-bias) -- load just that half of the weight tile
+            const int brow = den_kind ? nt * P.BN + (kb < P.den_kb_h ? P.BN / 2 : 0) : wrow0 + t * p.Np + nt * P.BN;
+            tma_load_2d(sa + TC_A_BYTES, &tmB, bar_full(stage), c0, brow);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
@@ -659,10 +659,13 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + TC_A_BYTES);
+          // denoiser: half-width MMA into the (main, skip) or the (gate, hyper-bias) column block of the accumulator
+          const uint32_t d_blk = den_kind ? d_tmem + (uint32_t)(kb < P.den_kb_h ? P.BN / 2 : 0) : d_tmem;
+          const bool first_kb = den_kind ? (kb == kb0 || kb == P.den_kb_h) : kb == kb0;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {  // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
-            if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (!first_kb || k > 0) ? 1u : 0u);
+            else umma_bf16(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (!first_kb || k > 0) ? 1u : 0u);
           }
           if (CG == 2) umma_commit_2sm(bar_empty(stage)); else umma_commit(bar_empty(stage));  // frees the smem slot
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
@@ -785,11 +788,10 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     } else if (den_kind) {
-      // ---- denoiser layer: quad-column epilogue, operand rows leave through a swizzled smem tile as 64-byte row pieces ----
+      // ---- denoiser layer: accumulator columns [gate Q | hyper-bias Q | main Q | skip Q], Q = BN/4 features per tile ----
       const DenEpi& d = p.epi.den;
       const bool fin = p.epi.kind == EPI_DEN_FINAL;
-      const int cols_w = P.BN / NG;  // accumulator columns of this warp (128 of the 256-wide tile)
-      const uint32_t my_stage = staging + (uint32_t)(warp - 2) * 2048u;  // [32 rows][64 B], 16-byte chunks XOR-swizzled
+      const int Q = P.BN >> 2, nchunk = Q >> 4;  // 16-feature chunks; the NG warps of a lane quarter alternate over them
       int it = 0;
       for (int tile = unit; tile < total_tiles; tile += nunits, ++it) {
         int nt, sp;
@@ -797,56 +799,52 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int as = it & 1;
         mbar_wait_relaxed(bar_tfull(as), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t t_row = t_lane + (uint32_t)as * 256u + (uint32_t)(grp * cols_w);
-        const int n_w = nt * P.BN + grp * cols_w;  // first accumulator column of this warp
+        const uint32_t t_row = t_lane + (uint32_t)as * 256u;
 #pragma unroll 1
-        for (int c = 0; c < cols_w; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)c, v);
+        for (int ch = grp; ch < nchunk; ch += NG) {
+          const uint32_t t0 = t_row + (uint32_t)(ch << 4);
+          uint32_t vg[16], vh[16], vm[16], vs[16];
+          tmem_ld16(t0, vg);
+          tmem_ld16(t0 + (uint32_t)Q, vh);
+          tmem_ld16(t0 + (uint32_t)(2 * Q), vm);
+          tmem_ld16(t0 + (uint32_t)(3 * Q), vs);
           tmem_ld_wait();
-          float o[8];
+          const int f0 = nt * Q + (ch << 4);  // first output feature of this chunk
+          float o[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = den_out(v + 4 * q, den_bias + n_w + c + 4 * q);
+          for (int i = 0; i < 16; ++i) {
+            const float4 bq = *reinterpret_cast<const float4*>(den_bias + 4 * (f0 + i));   // (bg, 0, b, bs)
+            const float gate = __uint_as_float(vg[i]) + bq.x;
+            o[i] = fmaf(__uint_as_float(vm[i]) + bq.z, __fdividef(1.f, 1.f + __expf(-gate)),
+                        __uint_as_float(vh[i]) + __uint_as_float(vs[i]) + bq.w);
+          }
+          if (!rc.ok) continue;
           if (fin) {
-            if (rc.ok) {
-              den_final_quad(d, rc.b, (n_w + c) >> 2, o);
-              den_final_quad(d, rc.b, ((n_w + c) >> 2) + 4, o + 4);
-            }
-          } else {
-            uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float a = o[2 * q], b = o[2 * q + 1];
+            for (int j = 0; j < 4; ++j) den_final_quad(d, rc.b, f0 + 4 * j, o + 4 * j);
+          } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = o[2 * j], b = o[2 * j + 1];
               a = a > 0.f ? a : 0.01f * a;
               b = b > 0.f ? b : 0.01f * b;
-              w[q] = pack2(p.op_fp16, a, b);
+              w[j] = pack2(p.op_fp16, a, b);
             }
-            const uint32_t addr = my_stage + (uint32_t)lane * 64u + (uint32_t)((((c >> 5) ^ (lane >> 1)) & 3) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            // 16 features = 32 bytes of this lane's operand row: one full-sector 256-bit store per destination
+            uint16_t* o1 = reinterpret_cast<uint16_t*>(d.dst1) + (long long)rc.b * d.ld1 + d.off1 + f0;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o1), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                         "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            if (d.dst2) {
+              uint16_t* o2 = reinterpret_cast<uint16_t*>(d.dst2) + (long long)rc.b * d.ld2 + d.off2 + f0;
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o2), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                           "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(bar_tempty(as), 0u)); else mbar_arrive(bar_tempty(as)); }
-        if (!fin) {
-          const int f_w = n_w >> 2;  // first output feature of this warp's 32
-          const int nchunk = cols_w >> 5;  // 16-byte chunks per row piece (4 when cols_w = 128)
-          const int myb = rc.ok ? rc.b : -1;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // 4 lanes cover one row's 64 contiguous bytes; 8 rows per instruction
-            const int R = i * 8 + (lane >> 2), j = lane & 3;
-            const int bR = __shfl_sync(0xffffffffu, myb, R);
-            const uint32_t src = my_stage + (uint32_t)R * 64u + (uint32_t)(((j ^ (R >> 1)) & 3) << 4);
-            uint4 o4;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "r"(src) : "memory");
-            if (bR >= 0 && j < nchunk) {
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.dst1) + (long long)bR * d.ld1 + d.off1 + f_w + 8 * j) = o4;
-              if (d.dst2)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.dst2) + (long long)bR * d.ld2 + d.off2 + f_w + 8 * j) = o4;
-            }
-          }
-          __syncwarp();
-        }
       }
     } else {
       int it = 0;
@@ -908,6 +906,13 @@ static EncodeTiledFn get_encode() {
 
 int tc_available() { return get_encode() != nullptr; }
 
+// few chains: narrower N tiles spread one layer over more SMs and shorten each CTA's serial load -> MMA -> epilogue chain
+int tc_den_tile_width(int B, int Np) {
+  int bn = Np < 256 ? Np : 256;
+  while (bn > 64 && (long long)ceil_div(B, TC_BM) * (Np / bn) < 96) bn /= 2;
+  return bn;
+}
+
 struct TcLaunch {
   CUtensorMap tmA, tmB;
   TcParams P;
@@ -932,8 +937,8 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.BN = p.Np < 256 ? p.Np : 256;
   const bool den_kind = p.epi.kind == EPI_DEN_LAYER || p.epi.kind == EPI_DEN_FINAL;
   if (den_kind) {
-    // few chains: narrower N tiles spread one layer over more SMs and shorten each CTA's serial load -> MMA -> epilogue chain
-    while (P.BN > 64 && (long long)ceil_div(p.B, TC_BM) * (p.Np / P.BN) < 96) P.BN /= 2;
+    P.BN = tc_den_tile_width(p.B, p.Np);
+    if (p.epi.den.bn != P.BN) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: denoiser weights packed for tile width %d, launch uses %d", p.epi.den.bn, P.BN);
   }
   P.n_tiles = ceil_div(p.Np, P.BN);
   if (p.Hm * p.Wm >= TC_BM) {
@@ -977,16 +982,18 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   const int cg = (allow_2sm && ew == 8 && P.BN == 256 && p.Np % 256 == 0 && P.kb_per_split >= 16 && P.m_tiles >= 2) ? 2 : 1;
   P.fd_munits = make_fastdiv(ceil_div(P.m_tiles, cg));
   if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
+  if (den_kind) P.b_box_bytes /= 2; // denoiser: a k-block loads only the column block (half of the tile's rows) it feeds
   P.b_stage_bytes = (int)align_up(P.b_box_bytes, 1024);
   const int stage_bytes = TC_A_BYTES + P.b_stage_bytes;
-  if (den_kind && (P.BN % 64 || p.Np % P.BN || p.ksplit != 1 || p.ncls > 1))
+  if (den_kind && (P.BN % 64 || p.Np % P.BN || p.ksplit != 1 || p.ncls > 1 || p.epi.den.din % TC_BK || p.epi.den.din >= p.Cs))
     DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: denoiser epilogue needs 4*dout (%d) to be a multiple of 256", p.Np);
+  P.den_kb_h = den_kind ? p.epi.den.din / TC_BK : 0;
   // per-warp staging tiles, then (denoiser) the layer's bias quads
   P.bias_src = nullptr;
   P.bias_floats = 0;
   P.bias_off = 0;
   P.fd_bias = make_fastdiv(1);
-  if (den_kind) { P.bias_src = p.epi.den.bias4; P.bias_floats = p.Np; P.bias_off = ew * 2048; }
+  if (den_kind) { P.bias_src = p.epi.den.bias4; P.bias_floats = p.Np; P.bias_off = 0; }
   else if (P.stage_cols && p.epi.kind == EPI_FWD_ACT) {
     P.bias_src = p.epi.bias; P.bias_floats = p.epi.bias_mod; P.bias_off = -1;  // set below: right behind the staging tiles
     P.fd_bias = make_fastdiv(p.epi.bias_mod);
@@ -994,7 +1001,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   // the sign-from-activations dgrad variant (DAMC_TC_NOBITS) stashes activation rows in the staging tiles; every other
   // staged launch writes its rows directly from registers and needs no tiles
   P.direct = (P.stage_cols && !(P.dbg & 4) && !(p.epi.kind == EPI_DGRAD_MASK && p.epi.maskbits == nullptr)) ? 1 : 0;
-  const int tiles_bytes = P.stage_cols ? (P.direct ? 0 : ew * TC_STAGING_PER_WARP) : den_kind ? ew * 2048 : 0;
+  const int tiles_bytes = P.stage_cols ? (P.direct ? 0 : ew * TC_STAGING_PER_WARP) : 0;
   auto stages_for = [&](int sb) { return std::min(TC_MAX_STAGES, (int)((227 * 1024 - 2048 - sb) / stage_bytes)); };
   if (!den_kind && stages_for(tiles_bytes + P.bias_floats * 4 + 128) < stages_for(tiles_bytes + 128))
     P.bias_floats = 0;  // a pipeline stage is worth more than the smem bias: the epilogue reads the bias through L1 instead
@@ -1004,7 +1011,8 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
   const uint32_t opfmt = fp16 ? 0u : 1u;  // kind::f16 operand format: 0 = f16, 1 = bf16
-  P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
+  const int mma_n = den_kind ? P.BN / 2 : P.BN;
+  P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
 
   CUtensorMap& tmA = L->tmA;
   CUtensorMap& tmB = L->tmB;
@@ -1024,7 +1032,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   {
     const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)(p.ncls > 1 ? p.ncls : 1) * p.ntaps * p.Np};
     const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(P.BN / cg)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(den_kind ? P.BN / 2 : P.BN / cg)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&tmB, tm_dtype, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
