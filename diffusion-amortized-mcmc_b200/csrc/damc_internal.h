@@ -57,6 +57,7 @@ struct DenEpi {
   int nz, residual, last, use_philox;
   float c_pred, c_eps, c_zt, c_x, c_std;
   unsigned long long seed, chain0, step;
+  const unsigned long long* seed_ptr;   // non-null: the Philox seed is read from device memory (replayed CUDA graphs)
 };
 
 struct Epilogue {
@@ -191,6 +192,13 @@ struct DenTcPack {
   void* Wq[DEN_NBN][DEN_LAYERS];  // [bn index][layer]: [4*dout][din+dout] operand type
   bool live[DEN_NBN] = {false, false, false};   // packed (and kept fresh by refill) once a launch has asked for it
   float* bias4[DEN_LAYERS];       // [4*dout] (bg, 0, b, bs)
+  // The T-step launch sequence (T x (1 + 7) kernels) of the last configuration seen twice, captured as a CUDA graph:
+  // everything it references lives in the caller's workspace (z is staged through ws.zbuf, the seed through
+  // ws.seed_dev) or in this handle, so it can be replayed as long as the key below matches.
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t cap_stream = nullptr;   // private stream the sequence is captured on (the caller's may be the legacy stream)
+  struct GraphKey { int B, T, use_philox; void* ws_base; unsigned long long chain0, coef_hash; } gkey = {0, 0, 0, nullptr, 0, 0};
+  int gkey_seen = 0;   // calls with gkey so far (the graph is captured on the second one)
 };
 
 struct DenPack : damc_handle {
@@ -217,6 +225,9 @@ struct DenPack : damc_handle {
 struct DenWs {   // carved out of the caller's workspace
   float *cx, *ct, *dlog, *coef;
   void* A[DEN_LAYERS];   // tcgen05 mode: layer operands [B][din+dout] (operand type); null in fp32 mode
+  float* zbuf;           // tcgen05 mode: [B][nz] staging copy of z for graph replays
+  unsigned long long* seed_dev;
+  void* base;
   size_t bytes;
 };
 DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base);

@@ -415,6 +415,9 @@ DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base) {
   w.coef = take(sizeof(float) * 8 * (size_t)T);
   for (int i = 0; i < DEN_LAYERS; ++i)
     w.A[i] = is_tc_precision(precision) ? (void*)take(2 * (size_t)B * (d->din[i] + d->dout[i])) : nullptr;
+  w.zbuf = is_tc_precision(precision) ? take(sizeof(float) * (size_t)B * d->nz) : nullptr;
+  w.seed_dev = is_tc_precision(precision) ? (unsigned long long*)take(16) : nullptr;
+  w.base = base;
   w.bytes = o;
   return w;
 }

@@ -50,6 +50,8 @@ __global__ void pack_den_bias4(const float* __restrict__ b, const float* __restr
 
 void den_tc_free(DenTcPack* t) {
   if (!t) return;
+  if (t->gexec) cudaGraphExecDestroy(t->gexec);
+  if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
   if (t->slab) cudaFree(t->slab);
   delete t;
 }
@@ -217,10 +219,10 @@ __global__ void __launch_bounds__(256) den_prep_kernel(const DenPrepArgs a, int 
 }
 
 // ---- driver -----------------------------------------------------------------------------------------------------------
-int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
-               const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
-               cudaStream_t s) {
-  DAMC_TRY(den_tc_ensure(d, precision, s));
+// issue the nsteps x (1 + 7) launches on stream s (directly, or into a stream capture)
+static int den_tc_issue(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
+                        const float* host_coef, const float* noise, int use_philox, uint64_t seed,
+                        const unsigned long long* seed_ptr, uint64_t chain0, cudaStream_t s) {
   const DenTcPack* t = d->tc[precision];
   // prepared launches: tensor maps are encoded once per call, the epilogue scalars of the last layer change per step
   TcLaunch* L[DEN_LAYERS] = {nullptr};
@@ -235,10 +237,6 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
     p.taps[0] = Tap{0, 0, 0, 0};
     p.N = p.Np = 4 * d->dout[i];
     const int bn = tc_den_tile_width(B, p.Np), v = den_bn_index(bn);
-    if (!t->live[v]) {   // first launch with this tile width: pack that row order now, refill() keeps it fresh afterwards
-      d->tc[precision]->live[v] = true;
-      DAMC_TRY(den_tc_pack_variant(d, precision, v, s));
-    }
     p.Wtc = t->Wq[v][i];
     p.ksplit = 1;
     p.epi.kind = i == DEN_LAYERS - 1 ? EPI_DEN_FINAL : EPI_DEN_LAYER;
@@ -254,7 +252,7 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
       }
     } else {
       e.z = z; e.eps_out = eps_out; e.nz = d->nz; e.residual = d->residual;
-      e.use_philox = use_philox; e.seed = seed; e.chain0 = chain0;
+      e.use_philox = use_philox; e.seed = seed; e.seed_ptr = seed_ptr; e.chain0 = chain0;
     }
     DAMC_TRY(tc_prepare(p, precision, &L[i]));
   }
@@ -265,7 +263,6 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
     pa.A[i] = w.A[i]; pa.ld[i] = d->din[i] + d->dout[i]; pa.din[i] = d->din[i]; pa.dout[i] = d->dout[i]; pa.coff[i] = d->coff[i];
   }
   const size_t prep_smem = sizeof(float) * ((size_t)d->nz * (d->nz / 2) + (size_t)EMB_PITCH * d->nz);
-  DAMC_CUDA(cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
   const int nb_embed = ceil_div(B, EMB_CHAINS), nb_ctx = ceil_div(B, CTX_CHAINS);
   for (int st = 0; st < nsteps; ++st) {
     const int irev = eps_out ? 0 : T - 1 - st;
@@ -296,8 +293,63 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
       if (r != DAMC_OK) return r;
     }
   }
-  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
+               const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
+               cudaStream_t s) {
+  DAMC_TRY(den_tc_ensure(d, precision, s));
+  DenTcPack* t = d->tc[precision];
+  // weight row orders for the tile widths this batch size uses (packed on first use, refreshed by refill())
+  for (int i = 0; i < DEN_LAYERS; ++i) {
+    const int v = den_bn_index(tc_den_tile_width(B, 4 * d->dout[i]));
+    if (!t->live[v]) { t->live[v] = true; DAMC_TRY(den_tc_pack_variant(d, precision, v, s)); }
+  }
+  const size_t prep_smem = sizeof(float) * ((size_t)d->nz * (d->nz / 2) + (size_t)EMB_PITCH * d->nz);
+  DAMC_CUDA(cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
   count_launch(2 + nsteps * (1 + DEN_LAYERS));
+
+  // ---- CUDA graph replay of the launch-bound T-step loop (Philox noise, whole sampler) ------------------------------
+  static const bool use_graph = []{ const char* e = getenv("DAMC_GRAPH"); return !(e && e[0] == '0'); }();
+  const bool graphable = use_graph && !profiling() && noise == nullptr && eps_out == nullptr && nsteps > 1 && w.zbuf && w.seed_dev;
+  if (!graphable) {
+    DAMC_TRY(den_tc_issue(d, precision, w, z, eps_out, B, T, nsteps, host_coef, noise, use_philox, seed, nullptr, chain0, s));
+    DAMC_CUDA(cudaGetLastError());
+    return DAMC_OK;
+  }
+  unsigned long long h = 1469598103934665603ull;   // FNV-1a over the step coefficients (schedule, var_type, with_noise)
+  for (size_t i = 0; i < 8 * (size_t)nsteps * sizeof(float); ++i) { h ^= reinterpret_cast<const unsigned char*>(host_coef)[i]; h *= 1099511628211ull; }
+  const DenTcPack::GraphKey key = {B, T, use_philox, w.base, (unsigned long long)chain0, h};
+  const bool same = t->gkey.B == key.B && t->gkey.T == key.T && t->gkey.use_philox == key.use_philox &&
+                    t->gkey.ws_base == key.ws_base && t->gkey.chain0 == key.chain0 && t->gkey.coef_hash == key.coef_hash;
+  if (!same) {   // new configuration: run it directly once; capture if it comes back
+    if (t->gexec) { cudaGraphExecDestroy(t->gexec); t->gexec = nullptr; }
+    t->gkey = key;
+    t->gkey_seen = 1;
+    DAMC_TRY(den_tc_issue(d, precision, w, z, eps_out, B, T, nsteps, host_coef, noise, use_philox, seed, nullptr, chain0, s));
+    DAMC_CUDA(cudaGetLastError());
+    return DAMC_OK;
+  }
+  ++t->gkey_seen;
+  if (!t->gexec) {
+    cudaGraph_t graph = nullptr;
+    if (!t->cap_stream) DAMC_CUDA(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = t->cap_stream;   // nothing executes during capture; the instantiated graph is launched on s
+    DAMC_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int r = den_tc_issue(d, precision, w, w.zbuf, nullptr, B, T, nsteps, host_coef, nullptr, use_philox, 0, w.seed_dev, chain0, cs);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (r != DAMC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess || !graph) DAMC_FAIL(DAMC_ERR_CUDA, "denoiser: stream capture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&t->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { t->gexec = nullptr; DAMC_FAIL(DAMC_ERR_CUDA, "denoiser: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+  }
+  const unsigned long long seed_host = seed;
+  DAMC_CUDA(cudaMemcpyAsync(w.seed_dev, &seed_host, sizeof(seed_host), cudaMemcpyHostToDevice, s));
+  DAMC_CUDA(cudaMemcpyAsync(w.zbuf, z, sizeof(float) * (size_t)B * d->nz, cudaMemcpyDeviceToDevice, s));
+  DAMC_CUDA(cudaGraphLaunch(t->gexec, s));
+  DAMC_CUDA(cudaMemcpyAsync(z, w.zbuf, sizeof(float) * (size_t)B * d->nz, cudaMemcpyDeviceToDevice, s));
   return DAMC_OK;
 }
 

@@ -259,7 +259,7 @@ __device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, c
       const float4 n4 = *reinterpret_cast<const float4*>(d.noise + zi);
       nrm[0] = n4.x; nrm[1] = n4.y; nrm[2] = n4.z; nrm[3] = n4.w;
     } else if (d.use_philox) {
-      philox_normal4(d.seed, d.chain0 + (unsigned long long)b, d.step, (uint32_t)(f0 >> 2), nrm);
+      philox_normal4(d.seed_ptr ? *d.seed_ptr : d.seed, d.chain0 + (unsigned long long)b, d.step, (uint32_t)(f0 >> 2), nrm);
     }
   }
 #pragma unroll

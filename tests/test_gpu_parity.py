@@ -378,6 +378,29 @@ def test_damc_tensor_core_matches_fp32_kernel_on_ragged_batches(B, dev):
         assert torch.equal(one[0], outs["fp16"][0])
 
 
+def test_damc_graph_replay_matches_direct_launches(dev):
+    """The tcgen05 DAMC loop is captured into a CUDA graph the second time a configuration is seen and replayed afterwards
+    (z staged through the workspace, Philox seed read from device memory).  Direct launches (call 1), the capturing call
+    (2) and replays (3+) must agree bit for bit; a new seed on a replay must give new noise, equal to a direct run's."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    T, nz, B = 16, 128, 96
+    Q = dn._netQ_U(nc=3, nz=nz, nxemb=1024, ntemb=128, nif=64, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
+                   logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10")
+    Q.load_state_dict(synth.module_state_like(Q, prefix="Q."))
+    Q = Q.to(dev).eval()
+    xemb = (0.5 * synth.det_normal("xe", (B, 1024))).to(dev)
+    zT = synth.det_normal("zT", (B, nz))
+    runs = [MCMC.damc_sample(Q, xemb=xemb, z_init=zT, seed=5, precision="fp16").cpu() for _ in range(4)]
+    for r in runs[1:]:
+        assert torch.equal(r, runs[0])
+    other = MCMC.damc_sample(Q, xemb=xemb, z_init=zT, seed=6, precision="fp16").cpu()       # replay, new seed
+    assert not torch.equal(other, runs[0])
+    # same seed-6 chains through direct launches: a different batch size is a different graph key (first call = direct)
+    xe2, z2 = torch.cat([xemb, xemb[:8]]).contiguous(), torch.cat([zT, zT[:8]])
+    direct = MCMC.damc_sample(Q, xemb=xe2, z_init=z2, seed=6, precision="fp16").cpu()
+    assert torch.equal(direct[:B], other)
+
+
 ENC_TOL = {"fp32": 2e-4, "fp16": 5e-3, "bf16": 3e-2}
 
 
