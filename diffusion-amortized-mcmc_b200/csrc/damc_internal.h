@@ -157,6 +157,7 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream);
 // prepared launches (tensor maps encoded once, replayed many times; the plan's epilogue scalars stay editable)
 struct TcLaunch;
 int tc_prepare(const GemmPlan& p, int precision, TcLaunch** out);
+int tc_encode_2d(void* tensor_map /* CUtensorMap* */, int fp16, const void* base, int cols, int rows, int box_rows);
 int tc_den_tile_width(int B, int Np);   // N tile width convgemm will use for a denoiser layer with Np = 4*dout columns
 GemmPlan* tc_plan(TcLaunch* l);
 int tc_launch(TcLaunch* l, cudaStream_t stream);
@@ -237,6 +238,13 @@ int den_tc_ensure(const DenPack* d, int precision, cudaStream_t stream);
 int den_tc_refill(const DenPack* d, int precision, cudaStream_t stream);
 void den_tc_free(DenTcPack* t);
 // coef: host table [nsteps][8] in execution order (c_pred, c_eps, c_zt, c_x, c_std, last)
+// denoiser_cluster.cu: all T reverse steps in ONE launch -- a 4-CTA cluster owns 128 chains, splits every layer's N tiles,
+// and synchronises layers with the hardware cluster barrier (operand rows travel through L2)
+bool den_cluster_supported(const DenPack* d, int B);
+int den_tc_pack_bn128(const DenPack* d, int precision, cudaStream_t stream);   // ensures the bn = 128 row order is packed
+int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
+                    const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
+                    cudaStream_t stream);
 int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
                const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                cudaStream_t stream);

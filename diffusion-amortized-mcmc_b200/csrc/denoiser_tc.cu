@@ -57,6 +57,7 @@ void den_tc_free(DenTcPack* t) {
 }
 
 static const int kDenBn[DEN_NBN] = {256, 128, 64};
+int den_tc_ensure(const DenPack* d, int precision, cudaStream_t s);
 static int den_bn_index(int bn) { return bn == 256 ? 0 : bn == 128 ? 1 : 2; }
 
 static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStream_t s) {
@@ -72,6 +73,13 @@ static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStrea
       pack_den_blocks<__nv_bfloat16><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__nv_bfloat16*)t->Wq[v][i]);
   }
   DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+int den_tc_pack_bn128(const DenPack* d, int precision, cudaStream_t s) {
+  DAMC_TRY(den_tc_ensure(d, precision, s));
+  DenTcPack* t = d->tc[precision];
+  if (!t->live[1]) { t->live[1] = true; DAMC_TRY(den_tc_pack_variant(d, precision, 1, s)); }
   return DAMC_OK;
 }
 
@@ -300,6 +308,8 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
                const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                cudaStream_t s) {
   DAMC_TRY(den_tc_ensure(d, precision, s));
+  if (den_cluster_supported(d, B))   // one launch for all T steps: 4-CTA clusters own 128 chains each (denoiser_cluster.cu)
+    return den_cluster_run(d, precision, w, z, eps_out, B, T, nsteps, host_coef, noise, use_philox, seed, chain0, s);
   DenTcPack* t = d->tc[precision];
   // weight row orders for the tile widths this batch size uses (packed on first use, refreshed by refill())
   for (int i = 0; i < DEN_LAYERS; ++i) {
