@@ -76,6 +76,7 @@ using namespace damc;
 extern "C" {
 
 int damc_version(void) { return 100; }
+int damc_selftest(void) { return tc_selftest_fastdiv(); }
 const char* damc_last_error(void) { return g_err; }
 
 long long damc_launch_count(void) { return g_launches.load(); }

@@ -163,6 +163,7 @@ GemmPlan* tc_plan(TcLaunch* l);
 int tc_launch(TcLaunch* l, cudaStream_t stream);
 void tc_free(TcLaunch* l);
 int tc_available();
+int tc_selftest_fastdiv();
 
 // weight packing -- gen_pack.cu
 enum PackMode { PK_FIRST_FWD, PK_FIRST_DGRAD, PK_UP_FWD, PK_UP_DGRAD, PK_SAME_FWD, PK_LAST_DGRAD_COL, PK_LAST_FWD_SCATTER };

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) enc_instnorm_kernel(const float* __restri
                                                            int H, int W, int C, int planar, float eps, float slope) {
   __shared__ double red[2][8][32];
   __shared__ float stat[2][32];
-  const int c = threadIdx.x & 31, pl = threadIdx.x >> 5, c0 = blockIdx.x * 32, b = blockIdx.y;
+  const int c = threadIdx.x & 31, pl = threadIdx.x >> 5, c0 = blockIdx.y * 32, b = blockIdx.x;   // images on grid.x (no 65 535 cap)
   const int HW = H * W;
   const float* src = raw + (size_t)b * HW * C + c0 + c;
   float s = 0.f, s2 = 0.f;
@@ -189,7 +189,7 @@ int EncPack::refill(cudaStream_t stream) {
 template <typename T>
 static int launch_instnorm(const EncPack* e, const EncLayer& y, const float* raw, void* out, int B, int planar,
                            cudaStream_t s) {
-  enc_instnorm_kernel<T><<<dim3(y.cout / 32, B), 256, 0, s>>>(raw, y.src.in_weight, y.src.in_bias, (T*)out, B, y.Hout,
+  enc_instnorm_kernel<T><<<dim3(B, y.cout / 32), 256, 0, s>>>(raw, y.src.in_weight, y.src.in_bias, (T*)out, B, y.Hout,
                                                                y.Wout, y.cout, planar, e->eps, e->slope);
   DAMC_CUDA(cudaGetLastError());
   count_launch();

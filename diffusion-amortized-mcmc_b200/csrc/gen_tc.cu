@@ -698,6 +698,24 @@ static EncodeTiledFn get_encode() {
 
 int tc_available() { return get_encode() != nullptr; }
 
+// host-side check of the magic-number division the kernel's tile / row decoding relies on (same formula as FastDiv::div)
+int tc_selftest_fastdiv() {
+  auto div = [](const FastDiv& f, int n) { return f.mul ? (int)((uint32_t)(((unsigned long long)(uint32_t)n * f.mul) >> 31) >> f.shr) : n; };
+  const int ns[] = {0, 1, 2, 3, 63, 64, 65, 127, 128, 1000, 4095, 4096, 65535, 65536, 1000003, (1 << 24) + 7, 0x7ffffffe, 0x7fffffff};
+  uint32_t x = 12345u;
+  for (int d = 1; d <= 70000; d = d < 4200 ? d + 1 : d + 977) {
+    const FastDiv f = make_fastdiv(d);
+    for (int n : ns)
+      if (div(f, n) != n / d) DAMC_FAIL(DAMC_ERR_INVALID, "FastDiv: %d / %d -> %d", n, d, div(f, n));
+    for (int i = 0; i < 64; ++i) {
+      x = x * 1664525u + 1013904223u;
+      const int n = (int)(x >> 1);
+      if (div(f, n) != n / d) DAMC_FAIL(DAMC_ERR_INVALID, "FastDiv: %d / %d -> %d", n, d, div(f, n));
+    }
+  }
+  return DAMC_OK;
+}
+
 // K-major operand matrix [rows][cols] (16-bit elements, cols contiguous) as a 2-D tensor map with a {64, box_rows} box and
 // the 128-byte swizzle the UMMA descriptors of this engine expect
 int tc_encode_2d(void* tensor_map, int fp16, const void* base, int cols, int rows, int box_rows) {

@@ -52,6 +52,7 @@ SIGNATURES = {
     "damc_pack_encoder": (_I, [C.POINTER(_P), _I, C.POINTER(ConvLayer), _I, _I, _F, _F, _I, _P]),
     "damc_encoder_workspace_bytes": (_SZ, [_P, _I]),
     "damc_encoder_forward": (_I, [_P, _P, _P, _I, _P, _SZ, _P]),
+    "damc_selftest": (_I, []),
     "damc_launch_count": (C.c_longlong, []),
     "damc_profile_enable": (_I, [_I]),
     "damc_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

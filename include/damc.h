@@ -154,6 +154,8 @@ int damc_encoder_forward(const damc_handle* enc, const float* x, float* xemb, in
  * damc_launch_count : cumulative number of kernels this library has launched in the calling process.
  * damc_profile_enable(1) : bracket every generator GEMM launch with a cudaEvent pair on its own stream;
  * damc_profile_collect : synchronise those events, return their summed duration (ms) and count, and reset.        */
+/* damc_selftest : host-only consistency checks of the library's index arithmetic (no GPU needed); 0 = ok. */
+int damc_selftest(void);
 long long damc_launch_count(void);
 int damc_profile_enable(int on);
 int damc_profile_collect(double* gemm_ms, long long* gemm_launches);

@@ -97,3 +97,9 @@ def test_encoder_family_detection(built_lib):
     assert not MCMC._encoder_on_library(enc, torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError, match="CUDA"):
         MCMC.encoder_forward(dn.Encoder("cifar10", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 32, 32), precision="bf16")
+
+
+def test_library_selftest(built_lib):
+    """Host-side check of the magic-number division behind the kernels' tile / row decoding (70 k divisors x 80 dividends
+    up to 2^31 - 1, against integer division)."""
+    built_lib.check(built_lib.lib().damc_selftest(), "damc_selftest")
