@@ -487,14 +487,29 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
   float zsq = 0.f, gsum = 0.f;
   if (tid < nz) {
     const float half_s2 = 0.5f * a.step * a.step;
+    // split-K partial sums of the generator gradient: 8 splits x CH chains = 32 independent loads per round trip, summed in
+    // ascending split order per chain (deterministic)
+    float gG[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gG[c] = 0.f;
+    if (a.gpart != nullptr) {
+      for (int s0 = 0; s0 < a.nsplit; s0 += 8) {
+        float v[8][CH];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < CH; ++c)
+            v[u][c] = (s0 + u < a.nsplit && c < nvalid) ? a.gpart[((size_t)(s0 + u) * a.B + (size_t)(c0 + c)) * a.gstride + tid] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) gG[c] += v[u][c];
+      }
+    }
     for (int c = 0; c < nvalid; ++c) {
       const size_t chain = (size_t)(c0 + c);
       float g = gE[c];
-      if (a.gpart != nullptr) {
-        float gg = 0.f;
-        for (int s = 0; s < a.nsplit; ++s) gg += a.gpart[((size_t)s * a.B + chain) * a.gstride + tid];
-        g = fmaf(gg, a.gpart_scale, g);
-      }
+      if (a.gpart != nullptr) g = fmaf(gG[c], a.gpart_scale, g);
       const float zv = zs[tid * CH + c];
       const float grad = g + zv;
       float nrm = 0.f;
