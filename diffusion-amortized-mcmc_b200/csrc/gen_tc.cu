@@ -767,7 +767,6 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
     P.BN = tc_den_tile_width(p.B, p.Np);
     if (p.epi.den.bn != P.BN) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: denoiser weights packed for tile width %d, launch uses %d", p.epi.den.bn, P.BN);
   }
-  P.n_tiles = ceil_div(p.Np, P.BN);
   if (p.Hm * p.Wm >= TC_BM) {
     P.Bt = 1;
     P.Ht = TC_BM / p.Wm;
@@ -779,6 +778,9 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
     P.tiles_per_img = 1;
     P.m_tiles = ceil_div(p.B, P.Bt);
   }
+  // (Tried: 256 x 128 pair tiles when 256 x 256 ones quantise badly, e.g. 3.46 waves at 128 chains.  They move 1.5x the
+  // L2 -> SM bytes per FLOP and the pair GEMMs are L2 -> SM bound: 21.9 ms vs 18.4 ms at 128 chains.  Dropped.)
+  P.n_tiles = ceil_div(p.Np, P.BN);
   P.tile_rows = p.Wm * P.Ht * P.Bt;
   auto log2_or_neg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
   P.wm_shift = log2_or_neg(p.Wm);
