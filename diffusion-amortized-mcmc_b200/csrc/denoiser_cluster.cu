@@ -58,6 +58,7 @@ struct DcParams {
   unsigned long long seed, chain0;
   int use_philox, residual;
   int B, T, nsteps, nz, csum, fp16, stages, bias_floats;
+  unsigned long long* tlog;   // dbg & 16: globaltimer stamps of cluster 0 / CTA 0 during step 1 (see tools/)
   int dbg;   // timing experiments (env DAMC_DC_DBG): 1 no ctx refresh, 2 no __threadfence, 4 no embedding, 8 no layer epilogue math
   uint32_t idesc;
 };
@@ -68,6 +69,9 @@ __device__ __forceinline__ uint16_t dc_cvt(bool fp16, float v) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   return *reinterpret_cast<const uint16_t*>(&h);
 }
+
+__device__ __forceinline__ unsigned long long dc_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DC_STAMP(slot) do { if (P.tlog && blockIdx.x == 0 && st == 1) P.tlog[(slot)] = dc_now(); } while (0)
 
 __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid_constant__ DcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -146,12 +150,22 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
 
   for (int st = 0; st < P.nsteps; ++st) {
     // ===================== operand preparation for this step (epilogue warps; this CTA's quarter of the chains) ==========
+    if (tid == 64) DC_STAMP(0);
     if (warp >= 2) {
       const int c0g = b0 + rank * DC_CHAINS;   // first global chain prepared by this CTA
       const int irev = P.eps_out ? 0 : P.T - 1 - st;
-      for (int i = et; i < DC_CHAINS * nz; i += 256) {
-        const int c = i / nz, k = i - c * nz;
-        zs[k * DC_ZP + c] = (c0g + c < P.B) ? P.z[(size_t)(c0g + c) * nz + k] : 0.f;
+      for (int i0 = et; i0 < DC_CHAINS * nz; i0 += 8 * 256) {   // 8 independent loads per round trip (z comes from L2)
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 256, c = i / nz;
+          v[u] = (i < DC_CHAINS * nz && c0g + c < P.B) ? P.z[(size_t)c0g * nz + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 256, c = i / nz, k = i - c * nz;
+          if (i < DC_CHAINS * nz) zs[k * DC_ZP + c] = v[u];
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       uint16_t* A0 = reinterpret_cast<uint16_t*>(P.A[0]);
@@ -189,11 +203,15 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
       // ctx activations: step 0 prepares every layer; later steps only the last layer's slice (the others were refreshed
       // during the previous step's layer phases, as soon as their readers were done)
       for (int l = (st == 0 ? 0 : DEN_LAYERS - 1); l < DEN_LAYERS; ++l) ctx_slice(l, irev);
-      __threadfence();
+      if (tid == 64) DC_STAMP(1);
+      // no __threadfence: every reader of these rows (TMA loads, z reads) is in this cluster, and the cluster barrier's
+      // release / acquire orders them at cluster scope; the proxy fence hands the generic-proxy writes to the async proxy
       fence_proxy_async_all();
+      if (tid == 64) DC_STAMP(2);
     }
     __syncwarp();
     cluster_sync_all();   // every CTA's operand rows are in L2
+    if (tid == 64) DC_STAMP(3);
 
     const float* cf = P.coef + (size_t)st * 8;
     for (int l = 0; l < DEN_LAYERS; ++l) {
@@ -202,6 +220,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
         // ===================== TMA producer =====================
         if (lane == 0) {
           fence_proxy_async_all();   // rows written through the generic proxy (by any CTA of the cluster) -> async-proxy reads
+          DC_STAMP(8 + 8 * l + 0);
           for (int nt = rank; nt < Ly.n_tiles; nt += DC_CL)
             for (int kb = 0; kb < Ly.kb_total; ++kb) {
               mbar_wait(bar_empty(stage), phase ^ 1u);
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
             const uint32_t d_tmem = tmem_base + (uint32_t)as * DC_BN;
             for (int kb = 0; kb < Ly.kb_total; ++kb) {
               mbar_wait(bar_full(stage), phase);
+              if (kb == 0 && nt == rank) DC_STAMP(8 + 8 * l + 1);
               tc_fence_after();
               const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
               const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + DC_A_BYTES);
@@ -237,6 +257,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
               if (++stage == P.stages) { stage = 0; phase ^= 1u; }
             }
             umma_commit(bar_tfull(as));
+            DC_STAMP(8 + 8 * l + 2);
           }
         }
       } else {
@@ -259,6 +280,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
         for (int nt = rank; nt < Ly.n_tiles; nt += DC_CL, ++acc_it) {
           const int as = acc_it & 1;
           mbar_wait(bar_tfull(as), (uint32_t)(acc_it >> 1) & 1u);
+          if (tid == 64) DC_STAMP(8 + 8 * l + 3);
           tc_fence_after();
           const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * DC_BN + (uint32_t)(grp << 4);
           uint32_t vg[16], vh[16], vm[16], vs[16];
@@ -304,11 +326,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
             }
           }
         }
-        if (!(P.dbg & 2)) __threadfence();
+        if (tid == 64) DC_STAMP(8 + 8 * l + 4);
+        if (P.dbg & 2) __threadfence();
         fence_proxy_async_all();
+        if (tid == 64) DC_STAMP(8 + 8 * l + 5);
       }
       __syncwarp();
       cluster_sync_all();   // layer l complete in every CTA of the cluster (its rows / the new z are visible in L2)
+      if (tid == 64) DC_STAMP(8 + 8 * l + 6);
     }
   }
   tc_fence_before();
@@ -323,7 +348,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
 // barriers, but each of its 4 CTAs streams the layer's operand rows and its quarter of the weights through a 144 KB ring
 // (~96 GB/s per SM at ~1.5 us L2 latency), so per step it costs about what the launch-bound per-layer path costs (69 us).
 // It wins while all clusters are resident at once and the per-layer launches are no longer latency-bound:
-// 1 024 <= B <= 37 clusters x 128 chains.  DAMC_DEN_CLUSTER=0 disables it, =2 forces it for every B.
+// 2 048 <= B <= 37 clusters x 128 chains (7.8 vs 8.9 ms at 4 096 chains; 7.1 vs 6.5 ms at 128).  DAMC_DEN_CLUSTER=0 disables
+// it, =2 forces it for every B.  Measured timeline of one step (DAMC_DC_DBG=16, profiles/r01_denoiser_cluster_timeline.txt):
+// operand preparation 10 us; per layer 0.5 us barrier + 0.5 us to the first TMA arrival + 0.3-0.38 us per 24 KB k-block
+// (the SM ingests ~80 GB/s whether or not the operand rows are multicast) + 1 us epilogue + 0.5 us proxy fence.
 bool den_cluster_supported(const DenPack* d, int B) {
   static const int mode = []{ const char* e = getenv("DAMC_DEN_CLUSTER"); return e ? atoi(e) : 1; }();
   if (mode == 0 || d->nz > 128 || d->nz % 8) return false;
@@ -332,7 +360,7 @@ bool den_cluster_supported(const DenPack* d, int B) {
   if (mode == 2) return true;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return B >= 1024 && ceil_div(B, DC_BM) <= sms / DC_CL;
+  return B >= 2048 && ceil_div(B, DC_BM) <= sms / DC_CL;
 }
 
 int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
@@ -363,6 +391,9 @@ int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, f
   P.z = z; P.eps_out = eps_out; P.noise = noise; P.seed = seed; P.chain0 = chain0; P.use_philox = use_philox;
   P.residual = d->residual; P.B = B; P.T = T; P.nsteps = nsteps; P.nz = d->nz; P.csum = d->csum; P.fp16 = fp16;
   P.dbg = getenv("DAMC_DC_DBG") ? atoi(getenv("DAMC_DC_DBG")) : 0;
+  static unsigned long long* tlog = nullptr;
+  if ((P.dbg & 16) && !tlog) { cudaMalloc(&tlog, 128 * 8); cudaMemset(tlog, 0, 128 * 8); }
+  P.tlog = (P.dbg & 16) ? tlog : nullptr;
   const uint32_t opfmt = fp16 ? 0u : 1u;
   P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)((DC_BN / 2) >> 3) << 17) | ((uint32_t)(DC_BM >> 4) << 24);
   const size_t fixed = 4 * ((size_t)d->nz * (d->nz / 2) + (size_t)d->nz * DC_ZP + boff) + 8 * (2 * 8 + 4) + 16 + 1024 + 64;
@@ -385,6 +416,18 @@ int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, f
   DAMC_CUDA(cudaLaunchKernelEx(&cfg, den_cluster_kernel, P));
   profile_mark(s, false);
   count_launch(3);
+  if (P.tlog) {   // experiment mode: dump the stamps of step 1 (ns relative to the step start)
+    unsigned long long h[128];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, P.tlog, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[dc] prep: compute %llu fence %llu barrier %llu\n", h[1] - h[0], h[2] - h[1], h[3] - h[2]);
+    for (int l = 0; l < DEN_LAYERS; ++l) {
+      const unsigned long long* e = h + 8 + 8 * l;
+      const unsigned long long start = l == 0 ? h[3] : h[8 + 8 * (l - 1) + 6];
+      fprintf(stderr, "[dc] layer %d: issue +%llu  first-full +%llu  mma-done +%llu  epi-wake +%llu  epi-done +%llu  fence +%llu  barrier +%llu\n", l,
+              e[0] - start, e[1] - start, e[2] - start, e[3] - start, e[4] - start, e[5] - start, e[6] - start);
+    }
+  }
   return DAMC_OK;
 }
 
