@@ -1,0 +1,81 @@
+"""Size-independent properties at BASELINE.json's full benchmark size (CIFAR-10 shape, nz = 128, ngf = 128, 1 024 chains,
+K = 30, bf16 tensor-core path) -- where the CPU oracle would take minutes, the domain's own invariants are checked instead:
+shard invariance (no collective inside sampling), determinism, energy descent of the noise-free sampler on an
+oracle-evaluated subset, and agreement of the tensor-core path with the fp32 CUDA-core path on that subset."""
+import pytest
+import torch
+
+from oracle import damc_oracle as O
+
+pytestmark = pytest.mark.gpu
+NZ, NGF, NC, B, K, SIGMA, STEP = 128, 128, 3, 1024, 30, 0.1, 0.1
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def problem(dev):
+    import bench
+    G, E = bench.make_nets(dev)           # default-init weights, seed 1: the benchmark's synthetic model
+    z0, x = bench.make_inputs(G, B, dev, 77)
+    return G, E, z0.to(dev), x
+
+
+def _run(problem, sl, **kw):
+    from damc_b200 import MCMC
+    G, E, z0, x = problem
+    z = z0[sl].clone().requires_grad_(True)
+    return MCMC.sample_langevin_post_z_with_prior(z, x[sl].contiguous(), G, E, K, SIGMA, kw.pop("noise_on", True), STEP,
+                                                  precision=kw.pop("precision", "bf16"), **kw)
+
+
+def test_shard_invariance_and_determinism_at_full_size(problem):
+    """1 024 chains in one call == the same chains as shards of 512 / 256+768 with their global chain offsets, bit for bit
+    (Philox keyed by the global chain index, rows of a GEMM tile independent, no cross-chain reduction anywhere)."""
+    full = _run(problem, slice(0, B), seed=11)
+    again = _run(problem, slice(0, B), seed=11)
+    assert torch.equal(full, again)
+    halves = torch.cat([_run(problem, slice(0, 512), seed=11, chain0=0), _run(problem, slice(512, B), seed=11, chain0=512)])
+    assert torch.equal(full, halves)
+    ragged = torch.cat([_run(problem, slice(0, 256), seed=11, chain0=0), _run(problem, slice(256, B), seed=11, chain0=256)])
+    assert torch.equal(full, ragged)
+    assert not torch.equal(full, _run(problem, slice(0, B), seed=12))
+
+
+def test_noise_free_sampler_descends_the_energy_at_full_size(problem):
+    """z <- z - s^2/2 grad U without noise must lower U = |G(z)-x|^2/(2 sigma^2) + E(z) + |z|^2/2 for (almost) every chain;
+    U is evaluated by the fp64 oracle on 16 of the 1 024 chains."""
+    import bench  # noqa: F401
+    G, E, z0, x = problem
+    out = _run(problem, slice(0, B), noise_on=False)
+    idx = torch.arange(0, B, B // 16)
+    gen = [(G.gen[2 * i].weight.detach().double().cpu(), G.gen[2 * i].bias.detach().double().cpu(), G.gen[2 * i].stride[0],
+            G.gen[2 * i].padding[0]) for i in range(4)]
+    ebm = [(E.ebm[2 * i].weight.detach().double().cpu(), E.ebm[2 * i].bias.detach().double().cpu()) for i in range(3)]
+
+    def U(z):
+        zz = z.double().cpu()
+        xh = O.gen_forward(gen, zz)
+        return ((xh - x[idx].double().cpu()) ** 2).sum(dim=(1, 2, 3)) / (2 * SIGMA ** 2) + O.ebm_forward(ebm, zz) + \
+            0.5 * (zz ** 2).sum(1)
+
+    u0, u1 = U(z0[idx]), U(out[idx])
+    print(f"U before {u0.mean():.1f} after {u1.mean():.1f}")
+    # U is dominated by the irreducible pixel noise |sigma n|^2 / (2 sigma^2) ~ 3072 / 2, so the descent is a few percent
+    assert (u1 < u0).all() and float((u0 - u1).mean()) > 5.0
+
+
+def test_tensor_core_path_tracks_fp32_path_at_full_size(problem):
+    """Same injected noise through both engines for the first 64 chains at full width: bf16 within the north-star 2e-2, fp16
+    tighter (default-init weight profile: well conditioned through K = 30)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    noise = torch.randn(K, 64, NZ, generator=g).to(problem[2].device)
+    ref = _run(problem, slice(0, 64), precision="fp32", noise=noise)
+    for prec, tol in (("bf16", 2e-2), ("fp16", 4e-3)):
+        out = _run(problem, slice(0, 64), precision=prec, noise=noise)
+        err = float((out - ref).abs().max() / ref.abs().max())
+        print(f"{prec} vs fp32 at full width, K = {K}: {err:.3e}")
+        assert err < tol, (prec, err)
