@@ -11,7 +11,8 @@
  *   - all tensors are contiguous fp32 in the reference's own layouts: z [B,nz] row-major, x [B,nc,H,W] (NCHW),
  *     ConvTranspose2d weight [Cin,Cout,kH,kW], Linear weight [out,in].
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and performs no host
- *     synchronisation.  Calls are re-entrant for distinct (stream, workspace) pairs.
+ *     synchronisation.  Calls are re-entrant for distinct (handle, stream, workspace) triples; one handle must not be
+ *     used by two host threads at the same time (it caches packed weights, prepared launches and a CUDA graph).
  *   - the caller owns every buffer including the workspace; handles own only their packed weights, until damc_free.
  *   - return value: 0 = ok, non-zero = error; damc_last_error() returns a thread-local message.
  *   - there is no CPU fallback and no backend dispatch: unsupported configurations are hard errors.
