@@ -1,5 +1,6 @@
 // damc_api.cu -- extern "C" entry points of libdamc_b200 (declared in include/damc.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <utility>
 #include <vector>
@@ -205,18 +206,60 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
   if (!workspace || workspace_bytes < ws.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
   if (K == 0) return DAMC_OK;
   const GenLayer& last = g->layers[g->nlayers - 1];
-  // unused im2col slots (image border taps, channel padding) must read as zero; live slots are rewritten every step
-  DAMC_CUDA(cudaMemsetAsync(ws.gcol, 0, elem_size(g->precision) * (size_t)B * last.Hin * last.Win * 64, s));
-  if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 4 * K, s));
   const int S = dz_splits(g, B);
-  for (int i = 0; i < K; ++i) {
-    float* tr = trace ? trace + 4 * (size_t)i : nullptr;
-    DAMC_TRY(generator_forward(g, ws, z, B, x, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, s));
-    DAMC_TRY(generator_dgrad(g, ws, B, s));
-    DAMC_TRY(launch_ebm_step(m, z, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
-                             chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
-                             1.0f / generator_grad_scale(g, sigma), g->nz, s));
+  // the K x (forward, likelihood gradient, dgrad, fused EBM + update) launches on stream st, directly or into a capture
+  auto issue = [&](float* zz, const float* xx, const unsigned long long* seed_ptr, cudaStream_t st) -> int {
+    // unused im2col slots (image border taps, channel padding) must read as zero; live slots are rewritten every step
+    DAMC_CUDA(cudaMemsetAsync(ws.gcol, 0, elem_size(g->precision) * (size_t)B * last.Hin * last.Win * 64, st));
+    for (int i = 0; i < K; ++i) {
+      float* tr = trace ? trace + 4 * (size_t)i : nullptr;
+      DAMC_TRY(generator_forward(g, ws, zz, B, xx, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, st));
+      DAMC_TRY(generator_dgrad(g, ws, B, st));
+      DAMC_TRY(launch_ebm_step(m, zz, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
+                               chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
+                               1.0f / generator_grad_scale(g, sigma), g->nz, st, seed_ptr));
+    }
+    return DAMC_OK;
+  };
+  if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 4 * K, s));
+  // ---- CUDA-graph replay (tensor-core modes, Philox noise, no trace): no per-step host launches from the second call on --
+  static const bool use_graph = []{ const char* e = getenv("DAMC_GRAPH"); return !(e && e[0] == '0'); }();
+  const bool graphable = use_graph && g->use_tc && !profiling() && noise == nullptr && trace == nullptr &&
+                         x_hat_out == nullptr && K > 1;
+  if (!graphable) return issue(z, x, nullptr, s);
+  const GenPack::GraphKey key = {B, K, with_noise, step_size, sigma, (unsigned long long)chain0, (unsigned long long)step0,
+                                 ws.base, (const void*)m};
+  const GenPack::GraphKey& k0 = g->gkey;
+  const bool same = k0.B == key.B && k0.K == key.K && k0.with_noise == key.with_noise && k0.step == key.step &&
+                    k0.sigma == key.sigma && k0.chain0 == key.chain0 && k0.step0 == key.step0 && k0.ws_base == key.ws_base &&
+                    k0.ebm == key.ebm;
+  if (!same) {   // new configuration: run it directly once; capture if it comes back
+    if (g->gexec) { cudaGraphExecDestroy(g->gexec); g->gexec = nullptr; }
+    g->gkey = key;
+    return issue(z, x, nullptr, s);
   }
+  if (!g->gexec) {
+    if (!g->cap_stream) DAMC_CUDA(cudaStreamCreateWithFlags(&g->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    DAMC_CUDA(cudaStreamBeginCapture(g->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long long n0 = g_launches.load();
+    const int r = issue(ws.zbuf, ws.xbuf, ws.seed_dev, g->cap_stream);
+    g->graph_launches = g_launches.load() - n0;
+    g_launches -= g->graph_launches;   // nothing ran yet: replays are counted when they are launched
+    const cudaError_t ce = cudaStreamEndCapture(g->cap_stream, &graph);
+    if (r != DAMC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess || !graph) DAMC_FAIL(DAMC_ERR_CUDA, "posterior: stream capture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&g->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g->gexec = nullptr; DAMC_FAIL(DAMC_ERR_CUDA, "posterior: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+  }
+  const unsigned long long seed_host = seed;
+  DAMC_CUDA(cudaMemcpyAsync(ws.seed_dev, &seed_host, sizeof(seed_host), cudaMemcpyHostToDevice, s));
+  DAMC_CUDA(cudaMemcpyAsync(ws.zbuf, z, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, s));
+  DAMC_CUDA(cudaMemcpyAsync(ws.xbuf, x, sizeof(float) * (size_t)B * g->nc * g->H * g->W, cudaMemcpyDeviceToDevice, s));
+  DAMC_CUDA(cudaGraphLaunch(g->gexec, s));
+  count_launch((int)g->graph_launches);
+  DAMC_CUDA(cudaMemcpyAsync(z, ws.zbuf, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, s));
   return DAMC_OK;
 }
 

@@ -30,7 +30,8 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
 // single Langevin step for many chains with the MLP streamed from L2 (the posterior sampler's per-step tail)
 int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
                     uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
-                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream);
+                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream,
+                    const unsigned long long* seed_ptr = nullptr /* non-null: Philox seed read from device memory */);
 int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
 
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
@@ -131,7 +132,19 @@ struct GenPack : damc_handle {
   bool last_scatter = false;  // last layer runs as scatter-form GEMM + per-image finish kernel (image fits in smem)
   bool use_bits = false;    // tcgen05 engine: LeakyReLU masks travel as 1-bit-per-element words
   bool use_tc = false;      // bf16 mode: tcgen05 engine (default) or the SIMT engine on bf16 storage (DAMC_TC=0)
-  ~GenPack() override { for (void* p : allocs) cudaFree(p); }
+  // The K-step launch sequence of the posterior sampler (K x ~11 kernels) for the last configuration seen twice, as a
+  // CUDA graph: z, x and the Philox seed are staged through the caller's workspace, everything else it references is
+  // the workspace or this handle / the EBM handle, so it is replayed while the key matches.
+  struct GraphKey { int B, K, with_noise; float step, sigma; unsigned long long chain0, step0; void* ws_base; const void* ebm; };
+  mutable cudaGraphExec_t gexec = nullptr;
+  mutable cudaStream_t cap_stream = nullptr;
+  mutable GraphKey gkey = {0, 0, 0, 0.f, 0.f, 0, 0, nullptr, nullptr};
+  mutable long long graph_launches = 0;   // kernels in the captured sequence (for damc_launch_count on replays)
+  ~GenPack() override {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (void* p : allocs) cudaFree(p);
+  }
   int refill(cudaStream_t stream) override;
 };
 
@@ -143,6 +156,10 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
   void* gcol;                // [B*Hi*Wi][64]      T
   float* ybuf;               // [B*Hi*Wi][np_sc]   fp32 (scatter-form last layer) or null
   float* dz_part;            // [splits][B][nz_p]  fp32
+  float* zbuf;               // [B][nz] fp32: staging copy of z for graph replays
+  float* xbuf;               // [B][nc][H][W] fp32: staging copy of x for graph replays
+  unsigned long long* seed_dev;
+  void* base;
   size_t bytes;
 };
 

@@ -381,6 +381,7 @@ struct EbmStepArgs {
   int with_noise;
   const float* noise;  // [B,nz] for this step or null
   uint64_t seed, chain0, step_index;
+  const unsigned long long* seed_ptr;   // non-null: seed read from device memory (CUDA-graph replays)
   float* trace;        // null or [4]: sum E, (llhd), |z|^2/2, mean grad
   const float* gpart;
   int nsplit, gstride;
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
       const float grad = g + zv;
       float nrm = 0.f;
       if (a.with_noise)
-        nrm = a.noise ? a.noise[chain * nz + tid] : philox_normal1(a.seed, a.chain0 + chain, a.step_index, (uint32_t)tid);
+        nrm = a.noise ? a.noise[chain * nz + tid]
+                      : philox_normal1(a.seed_ptr ? *a.seed_ptr : a.seed, a.chain0 + chain, a.step_index, (uint32_t)tid);
       a.z[chain * nz + tid] = zv - half_s2 * grad + a.step * nrm;
       zsq += zv * zv;
       gsum += grad;
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
 
 int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
                     uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
-                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream) {
+                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream, const unsigned long long* seed_ptr) {
   constexpr int CH = 4;  // small chain tiles: two or more CTAs per SM overlap each other's L2 latency
   EbmStepArgs a{};
   a.use_ebm = m != nullptr;
@@ -547,6 +549,7 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
   }
   if (a.nz < 1 || a.nz > 256 || a.ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM step kernel: nz <= 256 and ndf <= 256 (nz=%d ndf=%d)", a.nz, a.ndf);
   a.z = z; a.B = B; a.step = step; a.with_noise = with_noise; a.noise = noise; a.seed = seed; a.chain0 = chain0;
+  a.seed_ptr = seed_ptr;
   a.step_index = step_index; a.trace = trace4; a.gpart = gpart; a.nsplit = nsplit; a.gstride = gstride;
   a.gpart_scale = gpart_scale;
   a.inv_count = 1.0f / ((float)B * (float)a.nz);

@@ -159,6 +159,10 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   ws->gcol = take(es * (size_t)B * last.Hin * last.Win * 64);
   ws->ybuf = g->last_scatter ? (float*)take(sizeof(float) * (size_t)B * last.Hin * last.Win * last.np_sc) : nullptr;
   ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(g, B) * B * g->nz_p);
+  ws->zbuf = (float*)take(sizeof(float) * (size_t)B * g->nz);
+  ws->xbuf = (float*)take(sizeof(float) * (size_t)B * g->nc * g->H * g->W);
+  ws->seed_dev = (unsigned long long*)take(16);
+  ws->base = base;
   ws->bytes = o;
   return DAMC_OK;
 }

@@ -35,9 +35,14 @@ def _run(problem, sl, **kw):
 def test_shard_invariance_and_determinism_at_full_size(problem):
     """1 024 chains in one call == the same chains as shards of 512 / 256+768 with their global chain offsets, bit for bit
     (Philox keyed by the global chain index, rows of a GEMM tile independent, no cross-chain reduction anywhere)."""
-    full = _run(problem, slice(0, B), seed=11)
-    again = _run(problem, slice(0, B), seed=11)
-    assert torch.equal(full, again)
+    full = _run(problem, slice(0, B), seed=11)           # direct launches
+    again = _run(problem, slice(0, B), seed=11)          # second call of the configuration: captured into a CUDA graph
+    third = _run(problem, slice(0, B), seed=11)          # replay
+    assert torch.equal(full, again) and torch.equal(full, third)
+    replay12 = _run(problem, slice(0, B), seed=12)       # replay with a new seed (read from device memory)
+    assert not torch.equal(full, replay12)
+    halves12 = torch.cat([_run(problem, slice(0, 512), seed=12, chain0=0), _run(problem, slice(512, B), seed=12, chain0=512)])
+    assert torch.equal(replay12, halves12)               # ... equals direct launches of the same chains
     halves = torch.cat([_run(problem, slice(0, 512), seed=11, chain0=0), _run(problem, slice(512, B), seed=11, chain0=512)])
     assert torch.equal(full, halves)
     ragged = torch.cat([_run(problem, slice(0, 256), seed=11, chain0=0), _run(problem, slice(256, B), seed=11, chain0=256)])
