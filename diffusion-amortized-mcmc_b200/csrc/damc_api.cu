@@ -72,6 +72,11 @@ int MlpPack::refill(cudaStream_t s) {
 
 }  // namespace damc
 
+unsigned long long damc_next_uid() {
+  static std::atomic<unsigned long long> next{1};
+  return next.fetch_add(1);
+}
+
 using namespace damc;
 
 extern "C" {
@@ -228,7 +233,7 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
                          x_hat_out == nullptr && K > 1;
   if (!graphable) return issue(z, x, nullptr, s);
   const GenPack::GraphKey key = {B, K, with_noise, step_size, sigma, (unsigned long long)chain0, (unsigned long long)step0,
-                                 ws.base, (const void*)m};
+                                 ws.base, m ? m->uid : 0ull};
   const GenPack::GraphKey& k0 = g->gkey;
   const bool same = k0.B == key.B && k0.K == key.K && k0.with_noise == key.with_noise && k0.step == key.step &&
                     k0.sigma == key.sigma && k0.chain0 == key.chain0 && k0.step0 == key.step0 && k0.ws_base == key.ws_base &&

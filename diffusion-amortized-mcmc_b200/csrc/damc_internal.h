@@ -2,8 +2,10 @@
 #pragma once
 #include "damc_common.cuh"
 
+unsigned long long damc_next_uid();
 struct damc_handle {
   int kind;
+  const unsigned long long uid = damc_next_uid();   // never reused: cached graphs key on it, not on the (recyclable) address
   virtual ~damc_handle() {}
   // re-read the caller's weight tensors recorded at pack time into the packed buffers (async on stream)
   virtual int refill(cudaStream_t stream) = 0;
@@ -135,10 +137,10 @@ struct GenPack : damc_handle {
   // The K-step launch sequence of the posterior sampler (K x ~11 kernels) for the last configuration seen twice, as a
   // CUDA graph: z, x and the Philox seed are staged through the caller's workspace, everything else it references is
   // the workspace or this handle / the EBM handle, so it is replayed while the key matches.
-  struct GraphKey { int B, K, with_noise; float step, sigma; unsigned long long chain0, step0; void* ws_base; const void* ebm; };
+  struct GraphKey { int B, K, with_noise; float step, sigma; unsigned long long chain0, step0; void* ws_base; unsigned long long ebm; };
   mutable cudaGraphExec_t gexec = nullptr;
   mutable cudaStream_t cap_stream = nullptr;
-  mutable GraphKey gkey = {0, 0, 0, 0.f, 0.f, 0, 0, nullptr, nullptr};
+  mutable GraphKey gkey = {0, 0, 0, 0.f, 0.f, 0, 0, nullptr, 0};
   mutable long long graph_launches = 0;   // kernels in the captured sequence (for damc_launch_count on replays)
   ~GenPack() override {
     if (gexec) cudaGraphExecDestroy(gexec);
