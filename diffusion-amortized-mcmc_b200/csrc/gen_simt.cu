@@ -244,7 +244,7 @@ __host__ __device__ inline FinishRange finish_range(int blk, int irb, int Hi, in
 
 // KK / SS: compile-time kernel size and stride (3,1 | 4,2) so the tap arithmetic has no integer divisions; 0,0 = generic.
 template <typename T, int KK, int SS>
-__global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
+__global__ void __launch_bounds__(384) last_finish_kernel(const FinishArgs aa) {
   FinishArgs a = aa;
   if (KK) { a.k = KK; a.stride = SS; a.pad = 1; }
   extern __shared__ __align__(16) float fsm[];
@@ -254,10 +254,11 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
   const int pitch = a.np + 1;                   // odd pitch: consecutive pixels (threads) fall into different banks
   float* Ys = fsm;                              // [(ib-ia+1)*Wi][np+1]
   float* gS = fsm + (((size_t)nyr * pitch + 3) & ~(size_t)3);   // [(ob-oa+1)*Wo][4]
-  __shared__ float red[8];
+  __shared__ float red[12];
   {
     const float4* src = reinterpret_cast<const float4*>(a.Y + ((size_t)b * a.Hi + R.ia) * a.Wi * a.np);
     const int q4 = a.np / 4, n4 = nyr * q4;
+    const int q4_shift = (q4 & (q4 - 1)) == 0 ? __ffs(q4) - 1 : -1;
     for (int i0 = tid; i0 < n4; i0 += 4 * blockDim.x) {  // 4 independent 16-byte loads in flight per thread
       float4 v[4];
 #pragma unroll
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * blockDim.x;
         if (i < n4) {
-          const int row = i / q4, c4 = (i - row * q4) * 4;
+          const int row = q4_shift >= 0 ? (i >> q4_shift) : i / q4, c4 = (i - row * q4) * 4;
           float* d = Ys + (size_t)row * pitch + c4;
           d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
         }
@@ -281,8 +282,10 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
   float loss_acc = 0.f;
   for (int pix = tid; pix < ngr; pix += blockDim.x) {
     const int oyl = pix / a.Wo, ox = pix - oyl * a.Wo, oy = R.oa + oyl;
-    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    float h[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < a.nc; ++c) h[c] = a.bias[c];
+    if (a.x)   // issued before the smem sums so that the global-load latency hides behind them
+      for (int c = 0; c < a.nc; ++c) xv[c] = __ldg(a.x + (((size_t)b * a.nc + c) * a.Ho + oy) * a.Wo + ox);
     const int kk = KK ? KK : a.k, ss = KK ? SS : a.stride;
 #pragma unroll
     for (int kh = 0; kh < (KK ? KK : 4); ++kh) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(256) last_finish_kernel(const FinishArgs aa) {
       const size_t xi = (((size_t)b * a.nc + c) * a.Ho + oy) * a.Wo + ox;
       if (a.xhat && own) a.xhat[xi] = xh;
       if (a.x) {
-        const float r = xh - a.x[xi];
+        const float r = xh - xv[c];
         g[c] = r * (a.inv_sigma2 * a.gscale) * (1.f - xh * xh);
         if (own) loss_acc += 0.5f * a.inv_sigma2 * r * r;
       }
@@ -394,9 +397,17 @@ int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, 
   a.irb = finish_irb(y);
   a.nblk = ceil_div(y.Hin, a.irb);
   const size_t smem = finish_smem_for(y, a.irb);
+  // one thread per gradient pixel of a block when that fits (k3-s1-p1 at 32 x 32: 10 rows x 32 = 320 pixels -- with 256
+  // threads a quarter of the block would idle at the barrier while 64 threads do a second pixel)
+  int max_ngr = 0;
+  for (int blk = 0; blk < a.nblk; ++blk) {
+    const FinishRange R = finish_range(blk, a.irb, y.Hin, y.Hout, y.k, y.stride, y.pad);
+    max_ngr = std::max(max_ngr, (R.ob - R.oa + 1) * y.Wout);
+  }
+  const int threads = (max_ngr > 256 && max_ngr <= 384) ? (max_ngr + 31) / 32 * 32 : 256;
   auto go = [&](auto kern) -> int {
     DAMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * a.nblk, 256, smem, stream>>>(a);
+    kern<<<B * a.nblk, threads, smem, stream>>>(a);
     DAMC_CUDA(cudaGetLastError());
     return DAMC_OK;
   };
