@@ -261,7 +261,7 @@ void den_tc_free(DenTcPack* t);
 // denoiser_cluster.cu: all T reverse steps in ONE launch -- a 4-CTA cluster owns 128 chains, splits every layer's N tiles,
 // and synchronises layers with the hardware cluster barrier (operand rows travel through L2)
 bool den_cluster_supported(const DenPack* d, int B);
-int den_tc_pack_bn128(const DenPack* d, int precision, cudaStream_t stream);   // ensures the bn = 128 row order is packed
+int den_tc_pack_bn(const DenPack* d, int precision, int variant, cudaStream_t stream);   // ensures the row order of tile width 256 / 128 / 64 (variant 0 / 1 / 2) is packed
 int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
                     const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                     cudaStream_t stream);

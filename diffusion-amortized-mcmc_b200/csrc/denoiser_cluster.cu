@@ -4,17 +4,21 @@
 // :463-533, ConcatSquashLinearSkipCtx :417-445; helpers diffusion_helper_func.py:36-70).  Same arithmetic as the per-layer
 // tcgen05 path of denoiser_tc.cu (16-bit GEMM operands, fp32 accumulation, fp32 z / phase / update), different schedule:
 //
-//   * the dependency between two layers is per 128-chain M tile, so a 4-CTA thread-block cluster owns one M tile for all T
-//     steps and needs no grid-wide ordering: the CTAs split every layer's N tiles (128 columns = 32 output features as
-//     [gate | hyper-bias | main | skip] column blocks), write the next layer's 16-bit operand rows to global memory (they
-//     stay in L2) and meet at the hardware cluster barrier; the next layer's TMA loads pick the rows up again.
-//     8 barriers per reverse step replace 8 dependent kernel launches (~8 us each with programmatic dependent launch).
-//   * per CTA: warp 0 = TMA producer (6-stage smem ring: 16 KB of operand rows + 8 KB = the 64 weight rows a k-block
-//     feeds), warp 1 = tcgen05.mma issuer (M = 128, N = 64 half-tile MMAs into the matching half of a TMEM accumulator,
-//     two accumulators), warps 2..9 = epilogue (tcgen05.ld, gate / bias / skip algebra, LeakyReLU, 256-bit row stores;
-//     last layer: eps = z + out and the reverse update of z with Philox or injected noise) and, between steps, the fp32
-//     operand preparation (input embedding [sin 2 pi zB, cos 2 pi zB, z] with p.B resident in smem, ctx activations
-//     SiLU(cx + ct[t])) for the CTA's quarter of the chains.
+//   * the dependency between two layers is per 128-chain M tile, so an 8-CTA thread-block cluster owns one M tile for all T
+//     steps and needs no grid-wide ordering: the CTAs split every layer's N tiles (64 columns = 16 output features as
+//     [gate | hyper-bias | main | skip] column blocks; 1 or 2 tiles per CTA), write the next layer's 16-bit operand rows
+//     to global memory (they stay in L2) and meet at the hardware cluster barrier; the next layer's TMA loads pick the
+//     rows up again.  8 barriers per reverse step replace 8 dependent kernel launches.
+//   * per CTA: warp 0 = TMA producer of the operand rows (its 16-row slice of every k-block, multicast into all eight
+//     smem rings; one load feeds both of the CTA's tiles), warp 2 = TMA producer of the weights (the 32 rows a k-block
+//     feeds, per tile), warp 1 = tcgen05.mma issuer (M = 128, N = 32 half-tile MMAs into the matching half of a TMEM
+//     accumulator; the two tiles' chains interleaved), warps 3..10 = epilogue (tcgen05.ld, gate / bias / skip algebra,
+//     LeakyReLU, 256-bit row stores; last layer: eps = z + out and the reverse update of z with Philox or injected noise)
+//     and, between steps, the fp32 operand preparation (input embedding [sin 2 pi zB, cos 2 pi zB, z] with p.B resident
+//     in smem, ctx activations SiLU(cx + ct[t])) for the CTA's 16 chains.
+//   * measured (profiles/r01_denoiser_cluster_timeline.txt): a k-block costs 0.34 us (1 tile) / 0.49 us (2 tiles) whatever
+//     its bytes, cluster size or number of TMA-issuing threads -- i.e. ~85 ns per tcgen05.mma instruction of the in-order
+//     issue thread at these tiny N; with 8 barriers (0.5 us) and 6 us of operand preparation a step costs ~60 us.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -27,19 +31,20 @@
 
 namespace damc {
 
-constexpr int DC_CL = 4;                 // CTAs per cluster
-constexpr int DC_BM = 128, DC_BN = 128;  // M tile (chains per cluster), N tile (accumulator columns)
+constexpr int DC_CL = 8;                 // CTAs per cluster (the portable maximum)
+constexpr int DC_BM = 128, DC_BN = 64;   // M tile (chains per cluster), N tile (accumulator columns of one tile)
 constexpr int DC_Q = DC_BN / 4;          // output features per N tile
+constexpr int DC_TPC = 2;                // at most 2 N tiles per CTA and layer (dout <= 256), both fed by ONE load of the operand rows
 constexpr int DC_BK = 64;
 constexpr int DC_A_BYTES = DC_BM * DC_BK * 2;         // 16 KB
-constexpr int DC_B_BYTES = (DC_BN / 2) * DC_BK * 2;   //  8 KB: the half of the weight tile a k-block feeds
-constexpr int DC_STAGE = DC_A_BYTES + DC_B_BYTES;
-constexpr int DC_THREADS = 64 + 256;
+constexpr int DC_B_BYTES = (DC_BN / 2) * DC_BK * 2;   //  4 KB: the half of one weight tile a k-block feeds
+constexpr int DC_STAGE = DC_A_BYTES + DC_TPC * DC_B_BYTES;   // 24 KB
+constexpr int DC_THREADS = 96 + 256;   // warp 0: operand-row TMA, warp 1: MMA issuer, warp 2: weight TMA, warps 3..10: epilogue
 constexpr int DC_CHAINS = DC_BM / DC_CL;              // chains prepared per CTA
 constexpr int DC_ZP = DC_CHAINS + 4;                  // pitch of the transposed z tile (16-byte aligned rows)
 
 struct DcLayer {
-  int kb_h, kb_total, n_tiles;          // k-blocks of the h part / all, N tiles (4*dout / 128)
+  int kb_h, kb_total, tpc;              // k-blocks of the h part / all, N tiles per CTA (4*dout / 64 / 8 = 1 or 2)
   int boff;                             // offset of this layer's bias quads inside the smem bias table (floats)
   void* dst1; int ld1, off1;            // leaky_relu(out) -> next layer's operand slice
   void* dst2; int ld2, off2;            // U-net skip copy, or null
@@ -86,7 +91,6 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (P.stages + s); };
   auto bar_tfull = [&](int a) { return bars + 8u * (2 * P.stages + a); };
-  auto bar_tempty = [&](int a) { return bars + 8u * (2 * P.stages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * P.stages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -99,10 +103,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
     for (int i = 0; i < DEN_LAYERS; ++i) { prefetch_tmap(&P.tmA[i]); prefetch_tmap(&P.tmB[i]); }
     // a stage is free when the MMAs of ALL CTAs of the cluster have read it (each peer multicasts operand rows into it)
     for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), DC_CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 8); }
+    mbar_init(bar_tfull(0), 1);   // one accumulator set per layer; the cluster barrier between layers orders its reuse
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);   // two accumulators of 128 columns
+  if (warp == 1) tmem_alloc(tmem_slot, 128);   // DC_TPC accumulators of 64 columns
   for (int i = tid; i < nz * half; i += DC_THREADS) Bs[i] = __ldg(P.Bp + i);
   for (int l = 0, o = 0; l < DEN_LAYERS; o += 4 * P.dout[l], ++l)
     for (int i = tid; i < 4 * P.dout[l]; i += DC_THREADS) sbias[o + i] = __ldg(P.bias4[l] + i);
@@ -114,8 +118,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
 
   int stage = 0;           // smem ring position (producer and MMA issuer each track their own copy)
   uint32_t phase = 0;
-  int acc_it = 0;          // accumulator use counter (MMA issuer and epilogue warps each track their own copy)
-  const int et = tid - 64; // epilogue thread index 0..255 (warps 2..9)
+  int acc_it = 0;          // layer phases done so far: parity of the accumulator-full barrier
+  const int et = tid - 96; // epilogue thread index 0..255 (warps 3..10)
 
   // c_L = SiLU(cx + ct[irev]) for this CTA's quarter of the chains, written into the [din, din+dout) slice of layer L's
   // operand rows.  Thread = 4 consecutive columns of up to 8 chains per pass: all loads of a pass are issued before use.
@@ -150,8 +154,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
 
   for (int st = 0; st < P.nsteps; ++st) {
     // ===================== operand preparation for this step (epilogue warps; this CTA's quarter of the chains) ==========
-    if (tid == 64) DC_STAMP(0);
-    if (warp >= 2) {
+    if (tid == 96) DC_STAMP(0);
+    if (warp >= 3) {
       const int c0g = b0 + rank * DC_CHAINS;   // first global chain prepared by this CTA
       const int irev = P.eps_out ? 0 : P.T - 1 - st;
       for (int i0 = et; i0 < DC_CHAINS * nz; i0 += 8 * 256) {   // 8 independent loads per round trip (z comes from L2)
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
           if (i < DC_CHAINS * nz) zs[k * DC_ZP + c] = v[u];
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
       uint16_t* A0 = reinterpret_cast<uint16_t*>(P.A[0]);
       for (int i = et; i < (DC_CHAINS / 8) * half && !(P.dbg & 4); i += 256) {   // phase 2 pi z.B in fp32: it reaches tens of radians
         const int cg = i / half, j = i - cg * half;
@@ -203,15 +207,15 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
       // ctx activations: step 0 prepares every layer; later steps only the last layer's slice (the others were refreshed
       // during the previous step's layer phases, as soon as their readers were done)
       for (int l = (st == 0 ? 0 : DEN_LAYERS - 1); l < DEN_LAYERS; ++l) ctx_slice(l, irev);
-      if (tid == 64) DC_STAMP(1);
+      if (tid == 96) DC_STAMP(1);
       // no __threadfence: every reader of these rows (TMA loads, z reads) is in this cluster, and the cluster barrier's
       // release / acquire orders them at cluster scope; the proxy fence hands the generic-proxy writes to the async proxy
       fence_proxy_async_all();
-      if (tid == 64) DC_STAMP(2);
+      if (tid == 96) DC_STAMP(2);
     }
     __syncwarp();
     cluster_sync_all();   // every CTA's operand rows are in L2
-    if (tid == 64) DC_STAMP(3);
+    if (tid == 96) DC_STAMP(3);
 
     const float* cf = P.coef + (size_t)st * 8;
     for (int l = 0; l < DEN_LAYERS; ++l) {
@@ -221,48 +225,65 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
         if (lane == 0) {
           fence_proxy_async_all();   // rows written through the generic proxy (by any CTA of the cluster) -> async-proxy reads
           DC_STAMP(8 + 8 * l + 0);
-          for (int nt = rank; nt < Ly.n_tiles; nt += DC_CL)
-            for (int kb = 0; kb < Ly.kb_total; ++kb) {
-              mbar_wait(bar_empty(stage), phase ^ 1u);
-              const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
-              mbar_expect_tx(bar_full(stage), DC_A_BYTES + DC_B_BYTES);
-              // every CTA of the cluster multiplies the same 128 operand rows: each loads its 32-row slice once and
-              // multicasts it into all four rings (L2 -> SM operand traffic / 4)
-              tma_load_2d_mcast(sa + (uint32_t)rank * (DC_A_BYTES / DC_CL), &P.tmA[l], bar_full(stage), kb * DC_BK,
-                                b0 + rank * (DC_BM / DC_CL), (uint16_t)((1u << DC_CL) - 1u));
-              tma_load_2d(sa + DC_A_BYTES, &P.tmB[l], bar_full(stage), kb * DC_BK, nt * DC_BN + (kb < Ly.kb_h ? DC_BN / 2 : 0));
-              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
-            }
+          for (int kb = 0; kb < Ly.kb_total; ++kb) {
+            mbar_wait(bar_empty(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
+            mbar_expect_tx(bar_full(stage), DC_A_BYTES + Ly.tpc * DC_B_BYTES);
+            // every CTA of the cluster multiplies the same 128 operand rows: each loads its 16-row slice once and
+            // multicasts it into all eight rings; the rows feed both of this CTA's N tiles
+            tma_load_2d_mcast(sa + (uint32_t)rank * (DC_A_BYTES / DC_CL), &P.tmA[l], bar_full(stage), kb * DC_BK,
+                              b0 + rank * (DC_BM / DC_CL), (uint16_t)((1u << DC_CL) - 1u));
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else if (warp == 2) {
+        // ===================== weight TMA producer (a second issuing thread: one thread sustains ~1 bulk-tensor copy per
+        // 0.15-0.19 us, which is what bounded the k-block rate when warp 0 issued the operand rows and the weights) ==========
+        if (lane == 0) {
+          for (int kb = 0; kb < Ly.kb_total; ++kb) {
+            mbar_wait(bar_empty(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
+            for (int t = 0; t < Ly.tpc; ++t)
+              tma_load_2d(sa + DC_A_BYTES + t * DC_B_BYTES, &P.tmB[l], bar_full(stage), kb * DC_BK,
+                          (rank + t * DC_CL) * DC_BN + (kb < Ly.kb_h ? DC_BN / 2 : 0));
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+          }
         }
       } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-          for (int nt = rank; nt < Ly.n_tiles; nt += DC_CL, ++acc_it) {
-            const int as = acc_it & 1;
-            mbar_wait(bar_tempty(as), ((uint32_t)(acc_it >> 1) & 1u) ^ 1u);
+          for (int kb = 0; kb < Ly.kb_total; ++kb) {
+            mbar_wait(bar_full(stage), phase);
+            if (kb == 0) DC_STAMP(8 + 8 * l + 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)as * DC_BN;
-            for (int kb = 0; kb < Ly.kb_total; ++kb) {
-              mbar_wait(bar_full(stage), phase);
-              if (kb == 0 && nt == rank) DC_STAMP(8 + 8 * l + 1);
-              tc_fence_after();
-              const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
-              const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + DC_A_BYTES);
-              const uint32_t d_blk = d_tmem + (uint32_t)(kb < Ly.kb_h ? DC_BN / 2 : 0);   // (main, skip) | (gate, hyper-bias)
-              const bool first_kb = kb == 0 || kb == Ly.kb_h;
+            const uint32_t sa = smem_base + (uint32_t)stage * DC_STAGE;
+            const uint64_t adesc = make_sdesc(sa);
+            const bool first_kb = kb == 0 || kb == Ly.kb_h;
+            // accumulator t, (main, skip) half for an h k-block, (gate, hyper-bias) half for a c k-block; the two tiles'
+            // MMAs are independent accumulation chains and are issued interleaved
+            const uint32_t d0 = tmem_base + (uint32_t)(kb < Ly.kb_h ? DC_BN / 2 : 0), d1 = d0 + (uint32_t)DC_BN;
+            const uint64_t bdesc0 = make_sdesc(sa + DC_A_BYTES), bdesc1 = make_sdesc(sa + DC_A_BYTES + DC_B_BYTES);
+            const uint32_t acc0 = first_kb ? 0u : 1u;
+            if (Ly.tpc == 2) {
+#pragma unroll
+              for (int k = 0; k < DC_BK / 16; ++k) {
+                umma_bf16(d0, adesc + (uint64_t)(2 * k), bdesc0 + (uint64_t)(2 * k), P.idesc, k > 0 ? 1u : acc0);
+                umma_bf16(d1, adesc + (uint64_t)(2 * k), bdesc1 + (uint64_t)(2 * k), P.idesc, k > 0 ? 1u : acc0);
+              }
+            } else {
 #pragma unroll
               for (int k = 0; k < DC_BK / 16; ++k)
-                umma_bf16(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (!first_kb || k > 0) ? 1u : 0u);
-              umma_commit_mcast(bar_empty(stage), (uint16_t)((1u << DC_CL) - 1u));
-              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                umma_bf16(d0, adesc + (uint64_t)(2 * k), bdesc0 + (uint64_t)(2 * k), P.idesc, k > 0 ? 1u : acc0);
             }
-            umma_commit(bar_tfull(as));
-            DC_STAMP(8 + 8 * l + 2);
+            umma_commit_mcast(bar_empty(stage), (uint16_t)((1u << DC_CL) - 1u));
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
+          umma_commit(bar_tfull(0));
+          DC_STAMP(8 + 8 * l + 2);
         }
       } else {
         // ===================== epilogue warps =====================
-        const int q = warp & 3, grp = (warp - 2) >> 2;   // TMEM lane quarter; the two warps of a quarter take one 16-feature chunk each
+        const int q = warp & 3, grp = (warp - 3) >> 2;   // TMEM lane quarter; the two warps of a quarter take one N tile each
         const int b = b0 + q * 32 + lane;
         const bool ok = b < P.B;
         const bool fin = l == DEN_LAYERS - 1;
@@ -277,12 +298,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
         // while the producer / MMA warps work on this layer: layer l-1's ctx slice for the NEXT step (its readers, the
         // TMA loads of layer l-1 in this step, finished before the cluster barrier that opened this phase)
         if (l > 0 && st + 1 < P.nsteps && !(P.dbg & 1)) ctx_slice(l - 1, P.T - 2 - st);
-        for (int nt = rank; nt < Ly.n_tiles; nt += DC_CL, ++acc_it) {
-          const int as = acc_it & 1;
-          mbar_wait(bar_tfull(as), (uint32_t)(acc_it >> 1) & 1u);
-          if (tid == 64) DC_STAMP(8 + 8 * l + 3);
+        // the two warps of a TMEM lane quarter take one N tile each (tile rank + grp * 8; 16 features)
+        for (int one = 0; one < 1; ++one) {
+          if (grp >= Ly.tpc) break;
+          const int nt = rank + grp * DC_CL;
+          mbar_wait(bar_tfull(0), (uint32_t)acc_it & 1u);
+          if (tid == 96) DC_STAMP(8 + 8 * l + 3);
           tc_fence_after();
-          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * DC_BN + (uint32_t)(grp << 4);
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * DC_BN);
           uint32_t vg[16], vh[16], vm[16], vs[16];
           tmem_ld16(t0, vg);
           tmem_ld16(t0 + (uint32_t)DC_Q, vh);
@@ -290,10 +313,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
           tmem_ld16(t0 + (uint32_t)(3 * DC_Q), vs);
           tmem_ld_wait();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty(as));   // accumulator values are in registers: the MMA issuer may reuse it
           if (P.dbg & 8) continue;
-          const int f0 = nt * DC_Q + (grp << 4);
+          const int f0 = nt * DC_Q;
           const float* sb = sbias + Ly.boff + 4 * f0;
           float o[16];
 #pragma unroll
@@ -326,47 +347,46 @@ __global__ void __launch_bounds__(DC_THREADS, 1) den_cluster_kernel(const __grid
             }
           }
         }
-        if (tid == 64) DC_STAMP(8 + 8 * l + 4);
+        if (tid == 96) DC_STAMP(8 + 8 * l + 4);
         if (P.dbg & 2) __threadfence();
         fence_proxy_async_all();
-        if (tid == 64) DC_STAMP(8 + 8 * l + 5);
+        if (tid == 96) DC_STAMP(8 + 8 * l + 5);
       }
+      ++acc_it;
       __syncwarp();
       cluster_sync_all();   // layer l complete in every CTA of the cluster (its rows / the new z are visible in L2)
-      if (tid == 64) DC_STAMP(8 + 8 * l + 6);
+      if (tid == 96) DC_STAMP(8 + 8 * l + 6);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
-// Policy (measured, T = 100, profiles/r01_denoiser_timings.txt): the cluster kernel replaces 8 launches per step by 8 cluster
-// barriers, but each of its 4 CTAs streams the layer's operand rows and its quarter of the weights through a 144 KB ring
-// (~96 GB/s per SM at ~1.5 us L2 latency), so per step it costs about what the launch-bound per-layer path costs (69 us).
-// It wins while all clusters are resident at once and the per-layer launches are no longer latency-bound:
-// 2 048 <= B <= 37 clusters x 128 chains (7.8 vs 8.9 ms at 4 096 chains; 7.1 vs 6.5 ms at 128).  DAMC_DEN_CLUSTER=0 disables
-// it, =2 forces it for every B.  Measured timeline of one step (DAMC_DC_DBG=16, profiles/r01_denoiser_cluster_timeline.txt):
-// operand preparation 10 us; per layer 0.5 us barrier + 0.5 us to the first TMA arrival + 0.3-0.38 us per 24 KB k-block
-// (the SM ingests ~80 GB/s whether or not the operand rows are multicast) + 1 us epilogue + 0.5 us proxy fence.
+// Policy (measured, T = 100, profiles/r01_denoiser_timings.txt): 6.0 ms at 128 chains and 6.1 ms at 1 024 against 6.5 / 7.0 ms
+// for the per-layer launches (CUDA-graph replayed); with more than 8 clusters in flight the clusters contend (12 ms at
+// 2 304 chains) and the per-layer path, which fills all SMs per layer, wins.  DAMC_DEN_CLUSTER=0 disables the kernel,
+// =2 forces it for every B.
 bool den_cluster_supported(const DenPack* d, int B) {
   static const int mode = []{ const char* e = getenv("DAMC_DEN_CLUSTER"); return e ? atoi(e) : 1; }();
   if (mode == 0 || d->nz > 128 || d->nz % 8) return false;
   for (int i = 0; i < DEN_LAYERS; ++i)
-    if (d->din[i] % 64 || d->dout[i] % 128) return false;   // 4*dout/128 N tiles must split evenly over the 4 CTAs (lockstep rings)
+    // 4*dout/64 N tiles must split evenly over the 8 CTAs (lockstep rings), at most DC_TPC per CTA
+    if (d->din[i] % 64 || d->dout[i] % 128 || d->dout[i] > 128 * DC_TPC) return false;
   if (mode == 2) return true;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return B >= 2048 && ceil_div(B, DC_BM) <= sms / DC_CL;
+  (void)sms;
+  return ceil_div(B, DC_BM) <= 8;
 }
 
 int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
                     const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                     cudaStream_t s) {
-  DAMC_TRY(den_tc_pack_bn128(d, precision, s));
+  DAMC_TRY(den_tc_pack_bn(d, precision, 2, s));
   const DenTcPack* t = d->tc[precision];
   DcParams P{};
   const int fp16 = precision == DAMC_PREC_FP16;
@@ -374,10 +394,10 @@ int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, f
   int boff = 0;
   for (int i = 0; i < DEN_LAYERS; ++i) {
     const int kt = d->din[i] + d->dout[i];
-    DAMC_TRY(tc_encode_2d(&P.tmA[i], fp16, w.A[i], kt, B, DC_BM / DC_CL));   // box = one CTA's 32-row slice
-    DAMC_TRY(tc_encode_2d(&P.tmB[i], fp16, t->Wq[1][i], kt, 4 * d->dout[i], DC_BN / 2));
+    DAMC_TRY(tc_encode_2d(&P.tmA[i], fp16, w.A[i], kt, B, DC_BM / DC_CL));   // box = one CTA's 16-row slice
+    DAMC_TRY(tc_encode_2d(&P.tmB[i], fp16, t->Wq[2][i], kt, 4 * d->dout[i], DC_BN / 2));   // bn = 64 row order
     DcLayer& L = P.L[i];
-    L.kb_h = d->din[i] / DC_BK; L.kb_total = kt / DC_BK; L.n_tiles = 4 * d->dout[i] / DC_BN; L.boff = boff;
+    L.kb_h = d->din[i] / DC_BK; L.kb_total = kt / DC_BK; L.tpc = 4 * d->dout[i] / DC_BN / DC_CL; L.boff = boff;
     boff += 4 * d->dout[i];
     if (i < DEN_LAYERS - 1) {
       L.dst1 = w.A[i + 1]; L.ld1 = d->din[i + 1] + d->dout[i + 1]; L.off1 = 0;

@@ -76,10 +76,10 @@ static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStrea
   return DAMC_OK;
 }
 
-int den_tc_pack_bn128(const DenPack* d, int precision, cudaStream_t s) {
+int den_tc_pack_bn(const DenPack* d, int precision, int v, cudaStream_t s) {
   DAMC_TRY(den_tc_ensure(d, precision, s));
   DenTcPack* t = d->tc[precision];
-  if (!t->live[1]) { t->live[1] = true; DAMC_TRY(den_tc_pack_variant(d, precision, 1, s)); }
+  if (!t->live[v]) { t->live[v] = true; DAMC_TRY(den_tc_pack_variant(d, precision, v, s)); }
   return DAMC_OK;
 }
 

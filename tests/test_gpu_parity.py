@@ -357,8 +357,8 @@ def test_damc_sampler_tensor_core_golden(name, prec, dev):
 
 @pytest.mark.parametrize("B", [1, 130, 1000, 2100, 2500])
 def test_damc_tensor_core_matches_fp32_kernel_on_ragged_batches(B, dev):
-    """Partial 128-row tiles, Philox noise keyed by the global chain index: the tcgen05 paths (per-layer launches below
-    2 048 chains, the one-launch cluster kernel from 2 048 chains up) and the persistent fp32 kernel draw the same normals,
+    """Partial 128-row tiles, Philox noise keyed by the global chain index: the tcgen05 paths (the one-launch cluster kernel up to
+    1 024 chains, per-layer launches above) and the persistent fp32 kernel draw the same normals,
     so T-step results agree to operand rounding; and a chain's result does not depend on B or on the path."""
     from damc_b200 import MCMC, diffusion_net as dn
     T, nz = 12, 128
