@@ -265,7 +265,6 @@ extern "C" int damc_pack_encoder(damc_handle** out, int nlayers, const damc_conv
   e->nc = L[0].cin; e->H = height; e->W = width;
   e->use_tc = is_tc_precision(precision);
   auto fail = [&](const char* msg, int i) { delete e; set_error("encoder layer %d: %s", i, msg); return DAMC_ERR_UNSUPPORTED; };
-  if (e->use_tc && !tc_available()) { delete e; DAMC_FAIL(DAMC_ERR_CUDA, "encoder: the tcgen05 engine needs cuTensorMapEncodeTiled from the driver"); }
   int H = height, W = width;
   e->layers.resize(nlayers);
   for (int i = 0; i < nlayers; ++i) {
@@ -291,6 +290,7 @@ extern "C" int damc_pack_encoder(damc_handle** out, int nlayers, const damc_conv
     H = y.Hout; W = y.Wout;
   }
   e->nemb = L[nlayers - 1].cout;
+  if (e->use_tc && !tc_available()) { delete e; DAMC_FAIL(DAMC_ERR_CUDA, "encoder: the tcgen05 engine needs cuTensorMapEncodeTiled from the driver"); }
   const int r = e->refill((cudaStream_t)stream);
   if (r != DAMC_OK) { delete e; return r; }
   *out = e;

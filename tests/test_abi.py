@@ -103,3 +103,29 @@ def test_library_selftest(built_lib):
     """Host-side check of the magic-number division behind the kernels' tile / row decoding (70 k divisors x 80 dividends
     up to 2^31 - 1, against integer division)."""
     built_lib.check(built_lib.lib().damc_selftest(), "damc_selftest")
+
+
+def test_c_abi_argument_validation_without_a_gpu(built_lib):
+    """Entry points reject bad handles / shapes with a status code and a message before any CUDA work (no GPU needed)."""
+    import ctypes as C
+    L = built_lib.lib()
+    err = lambda: L.damc_last_error().decode()
+    # null / wrong handles
+    assert L.damc_denoise(None, None, None, 4, 10, None, 1, 1, None, 0, 0, 0, None, 0, None) == 1 and "handle" in err()
+    assert L.damc_encoder_forward(None, None, None, 1, None, 0, None) == 1
+    assert L.damc_posterior_langevin(None, None, None, None, 1, 1, 0.1, 0.1, 1, None, 0, 0, 0, None, None, None, 0, None) == 1
+    assert L.damc_denoise_workspace_bytes(None, 4, 10, 1) == 0 and L.damc_encoder_workspace_bytes(None, 4) == 0
+    # encoder shapes outside the supported family: UNSUPPORTED (2) with the offending layer named
+    fake = C.c_void_p(0x1000)   # never dereferenced: shape validation comes first
+    def layers(specs):
+        arr = (built_lib.ConvLayer * len(specs))()
+        for i, (cin, cout, k, s, p) in enumerate(specs):
+            last = i == len(specs) - 1
+            arr[i] = built_lib.ConvLayer(cin, cout, k, s, p, fake, fake, None if last else fake, None if last else fake)
+        return arr
+    out = C.c_void_p()
+    bad_first = layers([(3, 64, 5, 1, 2), (64, 128, 4, 2, 1), (128, 128, 4, 1, 0)])
+    assert L.damc_pack_encoder(C.byref(out), 3, bad_first, 8, 8, 0.2, 1e-5, 1, None) == 2 and "layer 0" in err()
+    odd = layers([(1, 64, 3, 1, 1), (64, 128, 4, 2, 1), (128, 256, 4, 2, 1), (256, 128, 3, 1, 0)])   # 14 -> 7 -> 3: odd map
+    assert L.damc_pack_encoder(C.byref(out), 4, odd, 14, 14, 0.2, 1e-5, 1, None) == 2 and "odd" in err()
+    assert L.damc_pack_encoder(C.byref(out), 3, bad_first, 8, 8, 0.2, 1e-5, 7, None) == 1 and "precision" in err()
