@@ -265,10 +265,10 @@ struct StagedEpi {
           const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
-            float h0 = __uint_as_float(v[8 * g + 2 * t2]) + bb[2 * t2], h1 = __uint_as_float(v[8 * g + 2 * t2 + 1]) + bb[2 * t2 + 1];
-            if (h0 > 0.f) oword |= 1u << (8 * g + 2 * t2); else h0 *= e.slope;
-            if (h1 > 0.f) oword |= 1u << (8 * g + 2 * t2 + 1); else h1 *= e.slope;
-            w[t2] = pack2(p.op_fp16, h0, h1);
+            const float h0 = __uint_as_float(v[8 * g + 2 * t2]) + bb[2 * t2], h1 = __uint_as_float(v[8 * g + 2 * t2 + 1]) + bb[2 * t2 + 1];
+            const bool p0 = h0 > 0.f, p1 = h1 > 0.f;   // selects, not branches
+            oword |= (p0 ? 1u : 0u) << (8 * g + 2 * t2) | (p1 ? 1u : 0u) << (8 * g + 2 * t2 + 1);
+            w[t2] = pack2(p.op_fp16, p0 ? h0 : h0 * e.slope, p1 ? h1 : h1 * e.slope);
           }
         }
         if (direct) {
