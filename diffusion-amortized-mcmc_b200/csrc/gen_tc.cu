@@ -275,7 +275,11 @@ struct StagedEpi {
           // 8 columns = 16 bytes of this lane's own row; two g's make one 256-bit store (full 32-byte sectors)
           if (g & 1) {
             if (out_bits && !(dbg & 1)) {
-              const unsigned long long a = out_bits + 2ull * (unsigned long long)(n_base + c + 8 * (g - 1));
+              unsigned long long a = out_bits + 2ull * (unsigned long long)(n_base + c + 8 * (g - 1));
+              if (dbg & 32) {   // experiment: same store instructions, but confined to the first 1 MB of the output (stays in L2)
+                const unsigned long long base = (unsigned long long)p.epi.out;
+                a = base + ((a - base) & 0xFFFE0ull);
+              }
               asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(wprev[0]), "r"(wprev[1]),
                            "r"(wprev[2]), "r"(wprev[3]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
             }
