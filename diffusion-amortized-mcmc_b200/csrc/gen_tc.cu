@@ -276,9 +276,10 @@ struct StagedEpi {
           if (g & 1) {
             if (out_bits && !(dbg & 1)) {
               unsigned long long a = out_bits + 2ull * (unsigned long long)(n_base + c + 8 * (g - 1));
-              if (dbg & 32) {   // experiment: same store instructions, but confined to the first 1 MB of the output (stays in L2)
+              if (dbg & (32 | 64 | 128)) {   // experiment: same store instructions, confined to the first 1 / 32 / 256 MB of the output
                 const unsigned long long base = (unsigned long long)p.epi.out;
-                a = base + ((a - base) & 0xFFFE0ull);
+                const unsigned long long span = (dbg & 32) ? (1ull << 20) : (dbg & 64) ? (32ull << 20) : (256ull << 20);
+                a = base + ((a - base) & (span - 32ull));
               }
               asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(wprev[0]), "r"(wprev[1]),
                            "r"(wprev[2]), "r"(wprev[3]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
