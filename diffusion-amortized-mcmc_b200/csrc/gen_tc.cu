@@ -62,7 +62,8 @@ struct TcParams {
   int cls_inner;    // merged parity classes: class index is the fastest tile dimension
   int den_kb_h;     // denoiser launches: k-blocks [0, den_kb_h) carry the layer input h, the rest the ctx activation c
   int direct;       // staged-epilogue launches: lanes store their own row pieces with 256-bit stores, no smem staging tiles
-  int dbg;          // experiment switches (env DAMC_TC_DBG): 1 = skip the staged epilogue's global stores, 2 = skip its math
+  int dbg;          // experiment switches (env DAMC_TC_DBG, profiles/r01_epilogue_ablation.txt): 1 no global stores, 2 no epilogue
+                    // math, 4 smem-staged 16-byte stores instead of direct 256-bit ones, 32 / 64 / 128 stores confined to 1 / 32 / 256 MB
   int stage_cols;   // 0: per-thread row stores; 64 | 128: epilogue staged through smem for coalesced 16-byte rows
 };
 
