@@ -1,6 +1,7 @@
 // damc_api.cu -- extern "C" entry points of libdamc_b200 (declared in include/damc.h).
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <atomic>
 #include <utility>
 #include <vector>
@@ -57,17 +58,107 @@ static int check_sm100() {
   return DAMC_OK;
 }
 
-int MlpPack::refill(cudaStream_t s) {
-  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
-  DAMC_CUDA(cudaMemcpyAsync(W1, src[0], sizeof(float) * ndf * nz, k, s));
-  DAMC_CUDA(cudaMemcpyAsync(b1, src[1], sizeof(float) * ndf, k, s));
-  DAMC_CUDA(cudaMemcpyAsync(W2, src[2], sizeof(float) * ndf * ndf, k, s));
-  DAMC_CUDA(cudaMemcpyAsync(b2, src[3], sizeof(float) * ndf, k, s));
-  DAMC_CUDA(cudaMemcpyAsync(w3, src[4], sizeof(float) * ndf, k, s));
-  DAMC_CUDA(cudaMemcpyAsync(b3, src[5], sizeof(float), k, s));
-  DAMC_TRY(launch_transpose(W1, W1T, ndf, nz, s));
-  DAMC_TRY(launch_transpose(W2, W2T, ndf, ndf, s));
+void MlpPack::sources(std::vector<HashSrc>& out) const {
+  const size_t n[6] = {(size_t)ndf * nz, (size_t)ndf, (size_t)ndf * ndf, (size_t)ndf, (size_t)ndf, 1};
+  for (int i = 0; i < 6; ++i) out.push_back(HashSrc{src[i], (unsigned long long)n[i], 0ull});
+}
+
+int MlpPack::refill(cudaStream_t s, const int* dirty) {
+  DAMC_TRY(launch_gated_copy(W1, src[0], (size_t)ndf * nz, dirty, s));
+  DAMC_TRY(launch_gated_copy(b1, src[1], ndf, dirty, s));
+  DAMC_TRY(launch_gated_copy(W2, src[2], (size_t)ndf * ndf, dirty, s));
+  DAMC_TRY(launch_gated_copy(b2, src[3], ndf, dirty, s));
+  DAMC_TRY(launch_gated_copy(w3, src[4], ndf, dirty, s));
+  DAMC_TRY(launch_gated_copy(b3, src[5], 1, dirty, s));
+  DAMC_TRY(launch_transpose(src[0], W1T, ndf, nz, s, dirty));   // from the caller's tensors: no dependence on the copies above
+  DAMC_TRY(launch_transpose(src[2], W2T, ndf, ndf, s, dirty));
   return DAMC_OK;
+}
+
+// ---- change detection for damc_repack ------------------------------------------------------------------------------------
+// h = sum over all source elements of mix(bits, global element index)  (64-bit, order-independent, so blocks add atomically).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+  return x;
+}
+__global__ void __launch_bounds__(256) weights_hash_kernel(const HashSrc* __restrict__ tab, int ntab,
+                                                           unsigned long long* __restrict__ st, int store_only) {
+  unsigned long long acc = 0ull;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
+  for (int t = 0; t < ntab; ++t) {
+    const HashSrc s = tab[t];
+    const unsigned long long n4 = ((reinterpret_cast<unsigned long long>(s.p) & 15ull) == 0ull) ? s.n >> 2 : 0ull;
+    const uint4* p4 = reinterpret_cast<const uint4*>(s.p);
+    for (unsigned long long i = tid; i < n4; i += nth) {
+      const uint4 v = __ldg(p4 + i);
+      const unsigned long long k = (s.off + 4ull * i + 1ull) * 0x9E3779B97F4A7C15ull;
+      acc += mix64((((unsigned long long)v.y << 32) | v.x) ^ k) + mix64((((unsigned long long)v.w << 32) | v.z) ^ (k + 0x632BE59BD9B4E019ull));
+    }
+    const unsigned int* p1 = reinterpret_cast<const unsigned int*>(s.p);
+    for (unsigned long long i = 4ull * n4 + tid; i < s.n; i += nth)
+      acc += mix64((unsigned long long)__ldg(p1 + i) ^ ((s.off + i + 1ull) * 0xC2B2AE3D27D4EB4Full));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long part[8];
+  __shared__ bool is_last;
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0ull;
+    for (int w = 0; w < 8; ++w) b += part[w];
+    atomicAdd(&st[0], b);
+    __threadfence();
+    is_last = atomicAdd(&st[3], 1ull) == (unsigned long long)gridDim.x - 1ull;
+    if (is_last) {   // every block's sum has landed: compare with the hash the packed buffers were built from
+      __threadfence();
+      const unsigned long long total = atomicAdd(&st[0], 0ull);
+      *reinterpret_cast<int*>(&st[2]) = (store_only || total == st[1]) ? 0 : 1;
+      st[1] = total;
+      st[0] = 0ull;
+      st[3] = 0ull;
+    }
+  }
+}
+
+__global__ void gated_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n, const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int launch_gated_copy(float* dst, const float* src, size_t n, const int* dirty, cudaStream_t stream) {
+  if (n == 0) return DAMC_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 592);
+  gated_copy_kernel<<<blocks, 256, 0, stream>>>(dst, src, n, dirty);
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+static int launch_hash(damc_handle* h, int store_only, cudaStream_t stream) {
+  weights_hash_kernel<<<296, 256, 0, stream>>>(h->hash_tab, h->hash_n, h->hash_state, store_only);
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
+
+int handle_hash_init(damc_handle* h, cudaStream_t stream) {
+  std::vector<HashSrc> tab;
+  h->sources(tab);
+  if (tab.empty() || getenv("DAMC_REPACK_ALWAYS")) return DAMC_OK;
+  unsigned long long off = 0;
+  for (HashSrc& s : tab) { s.off = off; off += s.n; }
+  DAMC_CUDA(cudaMalloc(&h->hash_tab, sizeof(HashSrc) * tab.size()));
+  DAMC_CUDA(cudaMalloc(&h->hash_state, 4 * sizeof(unsigned long long)));
+  h->hash_n = (int)tab.size();
+  // pageable host source: the copy is staged before the call returns, so the local table may go out of scope
+  DAMC_CUDA(cudaMemcpyAsync(h->hash_tab, tab.data(), sizeof(HashSrc) * tab.size(), cudaMemcpyHostToDevice, stream));
+  DAMC_CUDA(cudaMemsetAsync(h->hash_state, 0, 4 * sizeof(unsigned long long), stream));
+  return launch_hash(h, 1, stream);
+}
+
+int handle_repack(damc_handle* h, cudaStream_t stream) {
+  if (!h->hash_tab) return h->refill(stream, nullptr);
+  DAMC_TRY(launch_hash(h, 0, stream));
+  return h->refill(stream, reinterpret_cast<const int*>(&h->hash_state[2]));
 }
 
 }  // namespace damc
@@ -108,7 +199,7 @@ int damc_profile_collect(double* gemm_ms, long long* gemm_launches) {
 
 int damc_repack(damc_handle* h, void* stream) {
   if (!h) DAMC_FAIL(DAMC_ERR_INVALID, "damc_repack: null handle");
-  return h->refill((cudaStream_t)stream);
+  return handle_repack(h, (cudaStream_t)stream);
 }
 
 int damc_free(damc_handle* h) {
@@ -137,7 +228,8 @@ int damc_pack_mlp(damc_handle** out, int nz, int ndf, const float* W1, const flo
   m->W2T = p;
   const float* srcs[6] = {W1, b1, W2, b2, W3, b3};
   for (int i = 0; i < 6; ++i) m->src[i] = srcs[i];
-  const int r = m->refill(s);
+  int r = m->refill(s, nullptr);
+  if (r == DAMC_OK) r = handle_hash_init(m, s);
   if (r != DAMC_OK) { delete m; return r; }
   *out = m;
   return DAMC_OK;
@@ -221,7 +313,7 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
       DAMC_TRY(generator_forward(g, ws, zz, B, xx, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, st));
       DAMC_TRY(generator_dgrad(g, ws, B, st));
       DAMC_TRY(launch_ebm_step(m, zz, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
-                               chain0, step0 + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
+                               seed_ptr ? 0 : chain0, (seed_ptr ? 0 : step0) + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
                                1.0f / generator_grad_scale(g, sigma), g->nz, st, seed_ptr));
     }
     return DAMC_OK;
@@ -229,43 +321,64 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
   if (trace) DAMC_CUDA(cudaMemsetAsync(trace, 0, sizeof(float) * 4 * K, s));
   // ---- CUDA-graph replay (tensor-core modes, Philox noise, no trace): no per-step host launches from the second call on --
   static const bool use_graph = []{ const char* e = getenv("DAMC_GRAPH"); return !(e && e[0] == '0'); }();
-  const bool graphable = use_graph && g->use_tc && !profiling() && noise == nullptr && trace == nullptr &&
-                         x_hat_out == nullptr && K > 1;
+  const bool graphable = use_graph && g->use_tc && !profiling() && noise == nullptr && trace == nullptr && K > 1;
   if (!graphable) return issue(z, x, nullptr, s);
-  const GenPack::GraphKey key = {B, K, with_noise, step_size, sigma, (unsigned long long)chain0, (unsigned long long)step0,
-                                 ws.base, m ? m->uid : 0ull};
-  const GenPack::GraphKey& k0 = g->gkey;
-  const bool same = k0.B == key.B && k0.K == key.K && k0.with_noise == key.with_noise && k0.step == key.step &&
-                    k0.sigma == key.sigma && k0.chain0 == key.chain0 && k0.step0 == key.step0 && k0.ws_base == key.ws_base &&
-                    k0.ebm == key.ebm;
-  if (!same) {   // new configuration: run it directly once; capture if it comes back
-    if (g->gexec) { cudaGraphExecDestroy(g->gexec); g->gexec = nullptr; }
-    g->gkey = key;
+  const GenPack::GraphKey key = {B, K, with_noise, x_hat_out != nullptr ? 1 : 0, step_size, sigma, ws.base, m ? m->uid : 0ull};
+  auto same = [&](const GenPack::GraphKey& k0) {
+    return k0.B == key.B && k0.K == key.K && k0.with_noise == key.with_noise && k0.want_xhat == key.want_xhat &&
+           k0.step == key.step && k0.sigma == key.sigma && k0.ws_base == key.ws_base && k0.ebm == key.ebm;
+  };
+  GenPack::GraphEntry* ent = nullptr;
+  for (GenPack::GraphEntry& e : g->graphs) if (same(e.key)) { ent = &e; break; }
+  if (!ent) {   // new configuration: run it directly once; it is captured if it comes back
+    if ((int)g->graphs.size() >= GenPack::kMaxGraphs) {   // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < g->graphs.size(); ++i) if (g->graphs[i].last_use < g->graphs[lru].last_use) lru = i;
+      if (g->graphs[lru].gexec) cudaGraphExecDestroy(g->graphs[lru].gexec);
+      g->graphs.erase(g->graphs.begin() + (long)lru);
+    }
+    GenPack::GraphEntry e;
+    e.key = key;
+    e.last_use = ++g->graph_clock;
+    g->graphs.push_back(e);
     return issue(z, x, nullptr, s);
   }
-  if (!g->gexec) {
+  ent->last_use = ++g->graph_clock;
+  float* const xhat_user = x_hat_out;
+  if (!ent->gexec) {
     if (!g->cap_stream) DAMC_CUDA(cudaStreamCreateWithFlags(&g->cap_stream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
     DAMC_CUDA(cudaStreamBeginCapture(g->cap_stream, cudaStreamCaptureModeThreadLocal));
     const long long n0 = g_launches.load();
+    x_hat_out = xhat_user ? ws.xhat_buf : nullptr;   // the captured sequence writes G(z) of the last step into the workspace
     const int r = issue(ws.zbuf, ws.xbuf, ws.seed_dev, g->cap_stream);
-    g->graph_launches = g_launches.load() - n0;
-    g_launches -= g->graph_launches;   // nothing ran yet: replays are counted when they are launched
+    x_hat_out = xhat_user;
+    ent->launches = g_launches.load() - n0;
+    g_launches -= ent->launches;   // nothing ran yet: replays are counted when they are launched
     const cudaError_t ce = cudaStreamEndCapture(g->cap_stream, &graph);
     if (r != DAMC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (ce != cudaSuccess || !graph) DAMC_FAIL(DAMC_ERR_CUDA, "posterior: stream capture failed: %s", cudaGetErrorString(ce));
-    const cudaError_t ie = cudaGraphInstantiate(&g->gexec, graph, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&ent->gexec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { g->gexec = nullptr; DAMC_FAIL(DAMC_ERR_CUDA, "posterior: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    if (ie != cudaSuccess) { ent->gexec = nullptr; DAMC_FAIL(DAMC_ERR_CUDA, "posterior: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    ++g->graph_captures;
   }
-  const unsigned long long seed_host = seed;
-  DAMC_CUDA(cudaMemcpyAsync(ws.seed_dev, &seed_host, sizeof(seed_host), cudaMemcpyHostToDevice, s));
+  const unsigned long long rng_host[3] = {seed, chain0, step0};
+  DAMC_CUDA(cudaMemcpyAsync(ws.seed_dev, rng_host, sizeof(rng_host), cudaMemcpyHostToDevice, s));
   DAMC_CUDA(cudaMemcpyAsync(ws.zbuf, z, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, s));
   DAMC_CUDA(cudaMemcpyAsync(ws.xbuf, x, sizeof(float) * (size_t)B * g->nc * g->H * g->W, cudaMemcpyDeviceToDevice, s));
-  DAMC_CUDA(cudaGraphLaunch(g->gexec, s));
-  count_launch((int)g->graph_launches);
+  DAMC_CUDA(cudaGraphLaunch(ent->gexec, s));
+  count_launch((int)ent->launches);
+  ++g->graph_replays;
   DAMC_CUDA(cudaMemcpyAsync(z, ws.zbuf, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, s));
+  if (xhat_user)
+    DAMC_CUDA(cudaMemcpyAsync(xhat_user, ws.xhat_buf, sizeof(float) * (size_t)B * g->nc * g->H * g->W, cudaMemcpyDeviceToDevice, s));
   return DAMC_OK;
+}
+
+long long damc_graph_replays(const damc_handle* gen) {
+  if (!gen || gen->kind != H_GEN) return -1;
+  return static_cast<const GenPack*>(gen)->graph_replays;
 }
 
 }  // extern "C"

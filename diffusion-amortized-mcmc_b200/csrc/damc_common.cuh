@@ -82,6 +82,9 @@ __device__ inline float philox_normal1(uint64_t seed, uint64_t chain, uint64_t s
   return v[elem & 3];
 }
 
+// gated refill kernels: nothing to do when the handle's source tensors are unchanged since the last pack
+__device__ __forceinline__ bool gate_clean(const int* dirty) { return dirty != nullptr && *dirty == 0; }
+
 __device__ inline float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -3,12 +3,26 @@
 #include "damc_common.cuh"
 
 unsigned long long damc_next_uid();
+// one caller-owned weight tensor of a handle (for the change-detection hash of damc_repack)
+struct HashSrc { const float* p; unsigned long long n, off; };
 struct damc_handle {
   int kind;
   const unsigned long long uid = damc_next_uid();   // never reused: cached graphs key on it, not on the (recyclable) address
-  virtual ~damc_handle() {}
-  // re-read the caller's weight tensors recorded at pack time into the packed buffers (async on stream)
-  virtual int refill(cudaStream_t stream) = 0;
+  // damc_repack change detection: a 64-bit hash of every source tensor is recomputed on the device (one launch, reads the
+  // weights once) and compared with the hash of the values the packed buffers were built from; the packing kernels are
+  // always enqueued but return at once when nothing changed (`dirty` flag in device memory) -- no host synchronisation.
+  HashSrc* hash_tab = nullptr;            // device copy of the source table
+  int hash_n = 0;
+  unsigned long long* hash_state = nullptr;   // device: [0] accumulator, [1] hash of the packed values, [2] dirty flag, [3] ticket
+  virtual ~damc_handle() {
+    if (hash_tab) cudaFree(hash_tab);
+    if (hash_state) cudaFree(hash_state);
+  }
+  // the caller's tensors this handle was packed from; empty = no change detection (refill always repacks)
+  virtual void sources(std::vector<HashSrc>& out) const { (void)out; }
+  // re-read the caller's weight tensors recorded at pack time into the packed buffers (async on stream).
+  // dirty: null = unconditionally; else device flag -- every kernel of the refill returns immediately when *dirty == 0.
+  virtual int refill(cudaStream_t stream, const int* dirty) = 0;
 };
 
 namespace damc {
@@ -22,8 +36,14 @@ struct MlpPack : damc_handle {
   const float* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller's tensors (for damc_repack)
   float* slab = nullptr;
   ~MlpPack() override { if (slab) cudaFree(slab); }
-  int refill(cudaStream_t stream) override;
+  int refill(cudaStream_t stream, const int* dirty) override;
+  void sources(std::vector<HashSrc>& out) const override;
 };
+
+// change detection (damc_api.cu)
+int handle_hash_init(damc_handle* h, cudaStream_t stream);   // after the first refill: record the hash of the packed values
+int handle_repack(damc_handle* h, cudaStream_t stream);      // hash -> dirty flag -> gated refill
+int launch_gated_copy(float* dst, const float* src, size_t n, const int* dirty, cudaStream_t stream);
 
 int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, int with_noise, const float* noise,
                         uint64_t seed, uint64_t chain0, uint64_t step0, float* trace, int trace_stride,
@@ -33,8 +53,9 @@ int launch_ebm_langevin(const MlpPack* m, float* z, int B, int K, float step, in
 int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
                     uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
                     float gpart_scale, int nz_if_no_ebm, cudaStream_t stream,
-                    const unsigned long long* seed_ptr = nullptr /* non-null: Philox seed read from device memory */);
-int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream);
+                    const unsigned long long* seed_ptr = nullptr /* non-null: {seed, chain0, step0} in device memory;
+                                                                      chain0 / step_index arguments are then relative */);
+int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream, const int* dirty = nullptr);
 
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
 // Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]
@@ -101,6 +122,7 @@ struct GemmPlan {
   int N, Np;                // logical / padded (multiple of 16) output columns
   int ksplit;               // >1: grid.z splits the K loop (EPI_DGRAD_Z only)
   int op_fp16;              // tcgen05 engine: operands / stored tensors are fp16 (else bf16); set by launch_gemm_tc
+  int op_f32;               // tcgen05 engine: operands / stored tensors are tf32-rounded fp32 (kind::tf32); set by launch_gemm_tc
   int ncls;                 // tcgen05 engine only: 4 = all output-parity classes of a k4-s2-p1 forward in ONE launch
                             // (taps and epilogue parity derived from the class; Wtc holds the 4 class blocks back to back)
   Epilogue epi;
@@ -137,17 +159,27 @@ struct GenPack : damc_handle {
   // The K-step launch sequence of the posterior sampler (K x ~11 kernels) for the last configuration seen twice, as a
   // CUDA graph: z, x and the Philox seed are staged through the caller's workspace, everything else it references is
   // the workspace or this handle / the EBM handle, so it is replayed while the key matches.
-  struct GraphKey { int B, K, with_noise; float step, sigma; unsigned long long chain0, step0; void* ws_base; unsigned long long ebm; };
-  mutable cudaGraphExec_t gexec = nullptr;
+  // A small LRU of such graphs (a training loop alternates e.g. 128 training chains and 500 evaluation chains); the Philox
+  // seed, chain offset and step offset are read from device memory, so they are NOT part of the key.
+  struct GraphKey { int B, K, with_noise, want_xhat; float step, sigma; void* ws_base; unsigned long long ebm; };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t gexec = nullptr;   // null until the key has been seen twice
+    long long launches = 0;            // kernels in the captured sequence (for damc_launch_count on replays)
+    unsigned long long last_use = 0;
+  };
+  static constexpr int kMaxGraphs = 4;
+  mutable std::vector<GraphEntry> graphs;
+  mutable unsigned long long graph_clock = 0;
   mutable cudaStream_t cap_stream = nullptr;
-  mutable GraphKey gkey = {0, 0, 0, 0.f, 0.f, 0, 0, nullptr, 0};
-  mutable long long graph_launches = 0;   // kernels in the captured sequence (for damc_launch_count on replays)
+  mutable long long graph_replays = 0, graph_captures = 0;
   ~GenPack() override {
-    if (gexec) cudaGraphExecDestroy(gexec);
+    for (GraphEntry& e : graphs) if (e.gexec) cudaGraphExecDestroy(e.gexec);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     for (void* p : allocs) cudaFree(p);
   }
-  int refill(cudaStream_t stream) override;
+  int refill(cudaStream_t stream, const int* dirty) override;
+  void sources(std::vector<HashSrc>& out) const override;
 };
 
 struct GenWorkspace {   // carved out of the caller's workspace for a given B
@@ -160,13 +192,17 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
   float* dz_part;            // [splits][B][nz_p]  fp32
   float* zbuf;               // [B][nz] fp32: staging copy of z for graph replays
   float* xbuf;               // [B][nc][H][W] fp32: staging copy of x for graph replays
-  unsigned long long* seed_dev;
+  float* xhat_buf;           // [B][nc][H][W] fp32: G(z) of the last step inside a replayed graph (copied out to the caller)
+  unsigned long long* seed_dev;   // {seed, chain0, step0} for replayed graphs
   void* base;
   size_t bytes;
 };
 
 size_t elem_size(int precision);
+// 16-bit operand modes (2-byte storage; generator, denoiser and encoder engines)
 static inline bool is_tc_precision(int precision) { return precision == DAMC_PREC_BF16 || precision == DAMC_PREC_FP16; }
+// modes whose generator GEMMs run on the tcgen05 engine (DAMC_PREC_TF32: fp32 containers, kind::tf32 MMAs)
+static inline bool is_gen_tc_precision(int precision) { return is_tc_precision(precision) || precision == DAMC_PREC_TF32; }
 int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws);
 
 // SIMT implicit GEMM (fp32 or bf16 storage, fp32 accumulate) -- gen_simt.cu
@@ -187,7 +223,8 @@ int tc_selftest_fastdiv();
 // weight packing -- gen_pack.cu
 enum PackMode { PK_FIRST_FWD, PK_FIRST_DGRAD, PK_UP_FWD, PK_UP_DGRAD, PK_SAME_FWD, PK_LAST_DGRAD_COL, PK_LAST_FWD_SCATTER };
 int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int pad, int mode, int cls, int ntaps,
-                      int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream);
+                      int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream,
+                      const int* dirty = nullptr);
 size_t last_finish_smem(const GenLayer& y);
 int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
                        float inv_sigma2, float gscale, float* loss, void* gcol, cudaStream_t stream);
@@ -240,7 +277,8 @@ struct DenPack : damc_handle {
   damc_denoiser_desc src;                     // caller's tensors (for damc_repack)
   mutable DenTcPack* tc[3] = {nullptr, nullptr, nullptr};  // indexed by DAMC_PREC_*; built on first use, refilled by refill()
   ~DenPack() override;
-  int refill(cudaStream_t stream) override;
+  int refill(cudaStream_t stream, const int* dirty) override;
+  void sources(std::vector<HashSrc>& out) const override;
 };
 
 struct DenWs {   // carved out of the caller's workspace
@@ -255,7 +293,7 @@ DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base);
 
 // denoiser_tc.cu: the 7 layers of one reverse step as tcgen05 GEMMs (quad-column epilogue), all T steps
 int den_tc_ensure(const DenPack* d, int precision, cudaStream_t stream);
-int den_tc_refill(const DenPack* d, int precision, cudaStream_t stream);
+int den_tc_refill(const DenPack* d, int precision, cudaStream_t stream, const int* dirty = nullptr);
 void den_tc_free(DenTcPack* t);
 // coef: host table [nsteps][8] in execution order (c_pred, c_eps, c_zt, c_x, c_std, last)
 // denoiser_cluster.cu: all T reverse steps in ONE launch -- a 4-CTA cluster owns 128 chains, splits every layer's N tiles,

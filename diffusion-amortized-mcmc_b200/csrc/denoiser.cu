@@ -24,7 +24,8 @@ namespace damc {
 
 // ---- packing ------------------------------------------------------------------------------------------------------
 __global__ void pack_interleave_T(const float* __restrict__ A, const float* __restrict__ Bm, int rows, int cols,
-                                  float* __restrict__ dst) {  // A,B: [rows][cols] -> dst[cols][rows][2]
+                                  float* __restrict__ dst, const int* __restrict__ dirty) {  // A,B: [rows][cols] -> dst[cols][rows][2]
+  if (gate_clean(dirty)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int k = i / rows, o = i - k * rows;
@@ -32,7 +33,8 @@ __global__ void pack_interleave_T(const float* __restrict__ A, const float* __re
   dst[2 * i + 1] = Bm[(size_t)o * cols + k];
 }
 __global__ void pack_ctx_T(const float* __restrict__ Wc, int dout, int ntemb, int nxemb, int coff, int csum,
-                           float* __restrict__ dT, float* __restrict__ dX) {  // Wc [dout][ntemb+nxemb]
+                           float* __restrict__ dT, float* __restrict__ dX, const int* __restrict__ dirty) {  // Wc [dout][ntemb+nxemb]
+  if (gate_clean(dirty)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = ntemb + nxemb;
   if (i >= dout * w) return;
@@ -427,29 +429,40 @@ DenPack::~DenPack() {
   for (DenTcPack* t : tc) den_tc_free(t);
 }
 
-int DenPack::refill(cudaStream_t s) {
+void DenPack::sources(std::vector<HashSrc>& out) const {
   const damc_denoiser_desc* h = &src;
-  const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+  auto add = [&](const float* p, size_t n) { out.push_back(HashSrc{p, (unsigned long long)n, 0ull}); };
+  add(h->time_w1, (size_t)ntemb * ntemb); add(h->time_b1, ntemb); add(h->time_w2, (size_t)ntemb * ntemb); add(h->time_b2, ntemb);
+  add(h->Bproj, (size_t)nz * (nz / 2));
+  for (int i = 0; i < DEN_LAYERS; ++i) {
+    const size_t di = din[i], dn = dout[i];
+    add(h->W[i], dn * di); add(h->b[i], dn); add(h->Wc[i], dn * (ntemb + nxemb)); add(h->bc[i], dn);
+    add(h->Wg[i], dn * dn); add(h->bg[i], dn); add(h->Wb[i], dn * dn); add(h->Ws[i], dn * di); add(h->bs[i], dn);
+  }
+}
+
+int DenPack::refill(cudaStream_t s, const int* dirty) {
+  const damc_denoiser_desc* h = &src;
   const int nt = ntemb;
-  DAMC_CUDA(cudaMemcpyAsync(tw1, h->time_w1, sizeof(float) * nt * nt, dd, s));
-  DAMC_CUDA(cudaMemcpyAsync(tb1, h->time_b1, sizeof(float) * nt, dd, s));
-  DAMC_CUDA(cudaMemcpyAsync(tw2, h->time_w2, sizeof(float) * nt * nt, dd, s));
-  DAMC_CUDA(cudaMemcpyAsync(tb2, h->time_b2, sizeof(float) * nt, dd, s));
-  DAMC_CUDA(cudaMemcpyAsync(Bp, h->Bproj, sizeof(float) * nz * (nz / 2), dd, s));
-  DAMC_CUDA(cudaMemsetAsync(wstream, 0, sizeof(float) * stream_floats, s));  // row padding of the stream stays zero
+  DAMC_TRY(launch_gated_copy(tw1, h->time_w1, (size_t)nt * nt, dirty, s));
+  DAMC_TRY(launch_gated_copy(tb1, h->time_b1, nt, dirty, s));
+  DAMC_TRY(launch_gated_copy(tw2, h->time_w2, (size_t)nt * nt, dirty, s));
+  DAMC_TRY(launch_gated_copy(tb2, h->time_b2, nt, dirty, s));
+  DAMC_TRY(launch_gated_copy(Bp, h->Bproj, (size_t)nz * (nz / 2), dirty, s));
+  // (the row padding of the weight stream is zeroed once at pack time; the packing kernels never touch it)
   for (int i = 0; i < DEN_LAYERS; ++i) {
     const int di = din[i], dn = dout[i], off = coff[i];
-    pack_interleave_T<<<ceil_div(di * dn, 256), 256, 0, s>>>(h->W[i], h->Ws[i], dn, di, Wms[i]);
-    pack_interleave_T<<<ceil_div(dn * dn, 256), 256, 0, s>>>(h->Wg[i], h->Wb[i], dn, dn, Wgb[i]);
-    pack_ctx_T<<<ceil_div(dn * (nt + nxemb), 256), 256, 0, s>>>(h->Wc[i], dn, nt, nxemb, off, csum, WcT_t, WcT_x);
-    DAMC_CUDA(cudaMemcpyAsync(bias3[i], h->b[i], sizeof(float) * dn, dd, s));
-    DAMC_CUDA(cudaMemcpyAsync(bias3[i] + dn, h->bs[i], sizeof(float) * dn, dd, s));
-    DAMC_CUDA(cudaMemcpyAsync(bias3[i] + 2 * dn, h->bg[i], sizeof(float) * dn, dd, s));
-    DAMC_CUDA(cudaMemcpyAsync(bc + off, h->bc[i], sizeof(float) * dn, dd, s));
+    pack_interleave_T<<<ceil_div(di * dn, 256), 256, 0, s>>>(h->W[i], h->Ws[i], dn, di, Wms[i], dirty);
+    pack_interleave_T<<<ceil_div(dn * dn, 256), 256, 0, s>>>(h->Wg[i], h->Wb[i], dn, dn, Wgb[i], dirty);
+    pack_ctx_T<<<ceil_div(dn * (nt + nxemb), 256), 256, 0, s>>>(h->Wc[i], dn, nt, nxemb, off, csum, WcT_t, WcT_x, dirty);
+    DAMC_TRY(launch_gated_copy(bias3[i], h->b[i], dn, dirty, s));
+    DAMC_TRY(launch_gated_copy(bias3[i] + dn, h->bs[i], dn, dirty, s));
+    DAMC_TRY(launch_gated_copy(bias3[i] + 2 * dn, h->bg[i], dn, dirty, s));
+    DAMC_TRY(launch_gated_copy(bc + off, h->bc[i], dn, dirty, s));
   }
   DAMC_CUDA(cudaGetLastError());
   for (int prec = 0; prec < 3; ++prec)
-    if (tc[prec]) DAMC_TRY(den_tc_refill(this, prec, s));
+    if (tc[prec]) DAMC_TRY(den_tc_refill(this, prec, s, dirty));
   return DAMC_OK;
 }
 
@@ -515,7 +528,9 @@ extern "C" int damc_pack_denoiser(damc_handle** out, const damc_denoiser_desc* h
     d->Wms[i] = take(2 * (size_t)d->rows_ms[i] * d->dout[i]);
   }
   d->src = *h;
-  const int rr = d->refill(s);
+  if (cudaMemsetAsync(d->wstream, 0, sizeof(float) * d->stream_floats, s) != cudaSuccess) { delete d; DAMC_FAIL(DAMC_ERR_CUDA, "damc_pack_denoiser: memset failed"); }
+  int rr = d->refill(s, nullptr);
+  if (rr == DAMC_OK) rr = handle_hash_init(d, s);
   if (rr != DAMC_OK) { delete d; return rr; }
   if (den_stream_smem<16>(d, 3) > 227 * 1024) { delete d; DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "denoiser: kernel needs %zu B shared memory", den_stream_smem<16>(d, 3)); }
   *out = d;

@@ -27,7 +27,9 @@ namespace damc {
 // ---- packing: [4*dout][din+dout]; rows of N tile t (bn rows): [gate Q | hyper-bias Q | main Q | skip Q], Q = bn/4 -------
 template <typename T>
 __global__ void pack_den_blocks(const float* __restrict__ W, const float* __restrict__ Ws, const float* __restrict__ Wg,
-                                const float* __restrict__ Wb, int din, int dout, int bn, T* __restrict__ dst) {
+                                const float* __restrict__ Wb, int din, int dout, int bn, T* __restrict__ dst,
+                                const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
   const int Kt = din + dout, Q = bn >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4ll * dout * Kt) return;
@@ -42,7 +44,8 @@ __global__ void pack_den_blocks(const float* __restrict__ W, const float* __rest
   dst[i] = T(v);
 }
 __global__ void pack_den_bias4(const float* __restrict__ b, const float* __restrict__ bs, const float* __restrict__ bg,
-                               int dout, float* __restrict__ dst) {
+                               int dout, float* __restrict__ dst, const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= dout) return;
   reinterpret_cast<float4*>(dst)[n] = make_float4(bg[n], 0.f, b[n], bs[n]);
@@ -60,7 +63,7 @@ static const int kDenBn[DEN_NBN] = {256, 128, 64};
 int den_tc_ensure(const DenPack* d, int precision, cudaStream_t s);
 static int den_bn_index(int bn) { return bn == 256 ? 0 : bn == 128 ? 1 : 2; }
 
-static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStream_t s) {
+static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStream_t s, const int* dirty = nullptr) {
   DenTcPack* t = d->tc[precision];
   const damc_denoiser_desc* h = &d->src;
   for (int i = 0; i < DEN_LAYERS; ++i) {
@@ -68,9 +71,9 @@ static int den_tc_pack_variant(const DenPack* d, int precision, int v, cudaStrea
     const long long n = 4ll * dn * (di + dn);
     const int blocks = (int)((n + 255) / 256);
     if (precision == DAMC_PREC_FP16)
-      pack_den_blocks<__half><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__half*)t->Wq[v][i]);
+      pack_den_blocks<__half><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__half*)t->Wq[v][i], dirty);
     else
-      pack_den_blocks<__nv_bfloat16><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__nv_bfloat16*)t->Wq[v][i]);
+      pack_den_blocks<__nv_bfloat16><<<blocks, 256, 0, s>>>(h->W[i], h->Ws[i], h->Wg[i], h->Wb[i], di, dn, kDenBn[v], (__nv_bfloat16*)t->Wq[v][i], dirty);
   }
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
@@ -83,14 +86,14 @@ int den_tc_pack_bn(const DenPack* d, int precision, int v, cudaStream_t s) {
   return DAMC_OK;
 }
 
-int den_tc_refill(const DenPack* d, int precision, cudaStream_t s) {
+int den_tc_refill(const DenPack* d, int precision, cudaStream_t s, const int* dirty) {
   DenTcPack* t = d->tc[precision];
   if (!t) return DAMC_OK;
   const damc_denoiser_desc* h = &d->src;
   for (int v = 0; v < DEN_NBN; ++v)
-    if (t->live[v]) DAMC_TRY(den_tc_pack_variant(d, precision, v, s));
+    if (t->live[v]) DAMC_TRY(den_tc_pack_variant(d, precision, v, s, dirty));
   for (int i = 0; i < DEN_LAYERS; ++i)
-    pack_den_bias4<<<ceil_div(d->dout[i], 128), 128, 0, s>>>(h->b[i], h->bs[i], h->bg[i], d->dout[i], t->bias4[i]);
+    pack_den_bias4<<<ceil_div(d->dout[i], 128), 128, 0, s>>>(h->b[i], h->bs[i], h->bg[i], d->dout[i], t->bias4[i], dirty);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }

@@ -388,7 +388,7 @@ struct EbmStepArgs {
   int with_noise;
   const float* noise;  // [B,nz] for this step or null
   uint64_t seed, chain0, step_index;
-  const unsigned long long* seed_ptr;   // non-null: seed read from device memory (CUDA-graph replays)
+  const unsigned long long* seed_ptr;   // non-null: {seed, chain0, step0} read from device memory (CUDA-graph replays)
   float* trace;        // null or [4]: sum E, (llhd), |z|^2/2, mean grad
   const float* gpart;
   int nsplit, gstride;
@@ -523,7 +523,9 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
       float nrm = 0.f;
       if (a.with_noise)
         nrm = a.noise ? a.noise[chain * nz + tid]
-                      : philox_normal1(a.seed_ptr ? *a.seed_ptr : a.seed, a.chain0 + chain, a.step_index, (uint32_t)tid);
+                      : (a.seed_ptr   // replayed graphs: (seed, chain0, step0) live in device memory, step_index is relative
+                             ? philox_normal1(a.seed_ptr[0], a.seed_ptr[1] + chain, a.seed_ptr[2] + a.step_index, (uint32_t)tid)
+                             : philox_normal1(a.seed, a.chain0 + chain, a.step_index, (uint32_t)tid));
       a.z[chain * nz + tid] = zv - half_s2 * grad + a.step * nrm;
       zsq += zv * zv;
       gsum += grad;
@@ -567,7 +569,9 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
   return DAMC_OK;
 }
 
-__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                                 const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
   __shared__ float t[32][33];
   const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y)
@@ -578,8 +582,8 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     if (ox < rows && oy0 + r < cols) dst[(size_t)(oy0 + r) * rows + ox] = t[threadIdx.x][r];
 }
 
-int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream) {
-  transpose_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, stream>>>(src, dst, rows, cols);
+int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream, const int* dirty) {
+  transpose_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, stream>>>(src, dst, rows, cols, dirty);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }

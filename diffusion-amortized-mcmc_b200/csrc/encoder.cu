@@ -43,7 +43,8 @@ struct EncPack : damc_handle {
   std::vector<EncLayer> layers;
   std::vector<void*> allocs;
   ~EncPack() override { for (void* p : allocs) cudaFree(p); }
-  int refill(cudaStream_t stream) override;
+  int refill(cudaStream_t stream, const int* dirty) override;
+  void sources(std::vector<HashSrc>& out) const override;
 };
 
 struct EncWs {
@@ -164,7 +165,15 @@ static int enc_alloc(EncPack* e, void** p, size_t bytes) {
   return DAMC_OK;
 }
 
-int EncPack::refill(cudaStream_t stream) {
+void EncPack::sources(std::vector<HashSrc>& out) const {
+  // only the packed convolution weights are derived data; biases / InstanceNorm affines are read from the caller's tensors
+  for (int l = 1; l < nlayers; ++l) {
+    const EncLayer& y = layers[l];
+    out.push_back(HashSrc{y.src.weight, (unsigned long long)y.cout * y.cin * y.k * y.k, 0ull});
+  }
+}
+
+int EncPack::refill(cudaStream_t stream, const int* dirty) {
   const size_t es = elem_size(precision);
   for (int l = 1; l < nlayers; ++l) {
     EncLayer& y = layers[l];
@@ -176,11 +185,11 @@ int EncPack::refill(cudaStream_t stream) {
     if (use_tc) {
       if (!y.w_tc) DAMC_TRY(enc_alloc(this, &y.w_tc, n));
       DAMC_TRY(launch_pack_convt(y.src.weight, y.cout, y.cin, y.k, y.type == ENC_DOWN ? 2 : 1, y.type == ENC_DOWN ? 1 : 0, mode,
-                                 0, ntaps, Cs, y.cout, 1, precision, y.w_tc, stream));
+                                 0, ntaps, Cs, y.cout, 1, precision, y.w_tc, stream, dirty));
     } else {
       if (!y.w_simt) DAMC_TRY(enc_alloc(this, &y.w_simt, n));
       DAMC_TRY(launch_pack_convt(y.src.weight, y.cout, y.cin, y.k, y.type == ENC_DOWN ? 2 : 1, y.type == ENC_DOWN ? 1 : 0, mode,
-                                 0, ntaps, Cs, y.cout, 0, precision, y.w_simt, stream));
+                                 0, ntaps, Cs, y.cout, 0, precision, y.w_simt, stream, dirty));
     }
   }
   return DAMC_OK;
@@ -291,7 +300,8 @@ extern "C" int damc_pack_encoder(damc_handle** out, int nlayers, const damc_conv
   }
   e->nemb = L[nlayers - 1].cout;
   if (e->use_tc && !tc_available()) { delete e; DAMC_FAIL(DAMC_ERR_CUDA, "encoder: the tcgen05 engine needs cuTensorMapEncodeTiled from the driver"); }
-  const int r = e->refill((cudaStream_t)stream);
+  int r = e->refill((cudaStream_t)stream, nullptr);
+  if (r == DAMC_OK) r = handle_hash_init(e, (cudaStream_t)stream);
   if (r != DAMC_OK) { delete e; return r; }
   *out = e;
   return DAMC_OK;

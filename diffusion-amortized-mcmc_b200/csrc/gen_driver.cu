@@ -32,14 +32,14 @@ static int dev_alloc(GenPack* g, void** p, size_t bytes) {
 int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float slope, int precision,
                     cudaStream_t stream) {
   if (nlayers < 2 || nlayers > 8) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "generator needs 2..8 ConvTranspose2d layers (got %d)", nlayers);
-  if (precision != DAMC_PREC_FP32 && !is_tc_precision(precision)) DAMC_FAIL(DAMC_ERR_INVALID, "unknown precision %d", precision);
+  if (precision != DAMC_PREC_FP32 && !is_gen_tc_precision(precision)) DAMC_FAIL(DAMC_ERR_INVALID, "unknown precision %d", precision);
   g->kind = H_GEN;
   g->precision = precision;
   g->nlayers = nlayers;
   g->slope = slope;
   g->nz = L[0].cin;
   g->nz_p = (int)align_up(g->nz, 64);
-  const int cmult = is_tc_precision(precision) ? 64 : 16;
+  const int cmult = is_gen_tc_precision(precision) ? 64 : 16;
   int H = 1, W = 1;
   g->layers.resize(nlayers);
   for (int i = 0; i < nlayers; ++i) {
@@ -70,39 +70,58 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
 
   g->src.assign(L, L + nlayers);
   const char* env = getenv("DAMC_TC");
-  g->use_tc = is_tc_precision(precision) && !(env && env[0] == '0');
-  g->use_bits = g->use_tc && !getenv("DAMC_TC_NOBITS");
+  g->use_tc = is_gen_tc_precision(precision) && !(env && env[0] == '0');
+  g->use_bits = g->use_tc && (precision == DAMC_PREC_TF32 || !getenv("DAMC_TC_NOBITS"));
   if (g->use_tc && !tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "bf16 mode needs cuTensorMapEncodeTiled from the driver (no fallback)");
-  return g->refill(stream);
+  DAMC_TRY(g->refill(stream, nullptr));
+  return handle_hash_init(g, stream);
 }
 
-// (re)pack every layer's GEMM operands from the caller's ConvTranspose2d tensors; buffers are allocated on first use
-int GenPack::refill(cudaStream_t stream) {
+void GenPack::sources(std::vector<HashSrc>& out) const {
+  for (const damc_convt_layer& s : src) {
+    out.push_back(HashSrc{s.weight, (unsigned long long)s.cin * s.cout * s.k * s.k, 0ull});
+    if (s.bias) out.push_back(HashSrc{s.bias, (unsigned long long)s.cout, 0ull});
+  }
+}
+
+// (re)pack every layer's GEMM operands from the caller's ConvTranspose2d tensors; buffers are allocated on first use.
+// Only the layouts the chosen engine reads are packed: [tap][n][c] K-major for tcgen05, [tap][c][n] for the CUDA-core engine.
+int GenPack::refill(cudaStream_t stream, const int* dirty) {
   GenPack* g = this;
   const size_t es = elem_size(precision);
+  const bool simt = !use_tc;
   for (int i = 0; i < nlayers; ++i) {
     GenLayer& y = g->layers[i];
     const damc_convt_layer& s = g->src[i];
     const bool last = i == nlayers - 1;
     // bias (fp32 device copy)
-    if (!y.bias) DAMC_TRY(dev_alloc(g, (void**)&y.bias, sizeof(float) * s.cout));
-    if (s.bias) DAMC_CUDA(cudaMemcpyAsync(y.bias, s.bias, sizeof(float) * s.cout, cudaMemcpyDeviceToDevice, stream));
-    else DAMC_CUDA(cudaMemsetAsync(y.bias, 0, sizeof(float) * s.cout, stream));
+    if (!y.bias) {
+      DAMC_TRY(dev_alloc(g, (void**)&y.bias, sizeof(float) * s.cout));
+      DAMC_CUDA(cudaMemsetAsync(y.bias, 0, sizeof(float) * s.cout, stream));
+    }
+    if (s.bias) DAMC_TRY(launch_gated_copy(y.bias, s.bias, s.cout, dirty, stream));
     // forward operands
     int ntaps, Cs, mode, ncls = 1;
     if (y.type == L_FIRST) { ntaps = 1; Cs = y.cin_p; mode = PK_FIRST_FWD; y.n_fwd = s.k * s.k * s.cout; }
     else if (y.type == L_UP) { ntaps = 4; Cs = y.cin; mode = PK_UP_FWD; ncls = 4; y.n_fwd = s.cout; }
     else { ntaps = 9; Cs = y.cin; mode = PK_SAME_FWD; y.n_fwd = s.cout; }
     y.np_fwd = (int)align_up(y.n_fwd, 16);
-    for (int c = 0; c < ncls; ++c) {
-      if (!y.w_fwd[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
-      DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
-                                 precision, y.w_fwd[c], stream));
-      if (use_tc) {
+    if (last) {  // decided before the forward operands: the scatter form replaces the multi-tap forward of the last layer
+      y.n_sc = s.k * s.k * s.cout;
+      y.np_sc = (int)align_up(y.n_sc, 16);
+      const char* env = getenv("DAMC_LAST_SCATTER");
+      g->last_scatter = last_finish_smem(y) <= 200 * 1024 && !(env && env[0] == '0');
+    }
+    for (int c = 0; c < ncls && !(last && g->last_scatter); ++c) {
+      if (simt) {
+        if (!y.w_fwd[c]) DAMC_TRY(dev_alloc(g, &y.w_fwd[c], es * (size_t)ntaps * Cs * y.np_fwd));
+        DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 0,
+                                   precision, y.w_fwd[c], stream, dirty));
+      } else {
         if (!y.w_fwd_tc[0]) DAMC_TRY(dev_alloc(g, &y.w_fwd_tc[0], es * (size_t)ncls * ntaps * Cs * y.np_fwd));
         y.w_fwd_tc[c] = (char*)y.w_fwd_tc[0] + es * (size_t)c * ntaps * Cs * y.np_fwd;  // class blocks back to back
         DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, c, ntaps, Cs, y.np_fwd, 1,
-                                   precision, y.w_fwd_tc[c], stream));
+                                   precision, y.w_fwd_tc[c], stream, dirty));
       }
     }
     // dgrad operands
@@ -111,28 +130,24 @@ int GenPack::refill(cudaStream_t stream) {
     else { ntaps = 16; Cs = s.cout; mode = PK_UP_DGRAD; }
     y.n_dg = s.cin;
     y.np_dg = (int)align_up(y.n_dg, 16);
-    if (!y.w_dgrad) DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
-    DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 0,
-                               precision, y.w_dgrad, stream));
-    if (use_tc) {
+    if (simt) {
+      if (!y.w_dgrad) DAMC_TRY(dev_alloc(g, &y.w_dgrad, es * (size_t)ntaps * Cs * y.np_dg));
+      DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 0,
+                                 precision, y.w_dgrad, stream, dirty));
+    } else {
       if (!y.w_dgrad_tc) DAMC_TRY(dev_alloc(g, &y.w_dgrad_tc, es * (size_t)ntaps * Cs * y.np_dg));
       DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, mode, 0, ntaps, Cs, y.np_dg, 1,
-                                 precision, y.w_dgrad_tc, stream));
+                                 precision, y.w_dgrad_tc, stream, dirty));
     }
-    if (last) {  // scatter-form operands: one tap, N = k*k*nc
-      y.n_sc = s.k * s.k * s.cout;
-      y.np_sc = (int)align_up(y.n_sc, 16);
-      const char* env = getenv("DAMC_LAST_SCATTER");
-      g->last_scatter = last_finish_smem(y) <= 200 * 1024 && !(env && env[0] == '0');
-      if (g->last_scatter) {
+    if (last && g->last_scatter) {  // scatter-form operands: one tap, N = k*k*nc
+      if (simt) {
         if (!y.w_scatter) DAMC_TRY(dev_alloc(g, &y.w_scatter, es * (size_t)y.cin * y.np_sc));
         DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, PK_LAST_FWD_SCATTER, 0, 1, y.cin,
-                                   y.np_sc, 0, precision, y.w_scatter, stream));
-        if (use_tc) {
-          if (!y.w_scatter_tc) DAMC_TRY(dev_alloc(g, &y.w_scatter_tc, es * (size_t)y.cin * y.np_sc));
-          DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, PK_LAST_FWD_SCATTER, 0, 1, y.cin,
-                                     y.np_sc, 1, precision, y.w_scatter_tc, stream));
-        }
+                                   y.np_sc, 0, precision, y.w_scatter, stream, dirty));
+      } else {
+        if (!y.w_scatter_tc) DAMC_TRY(dev_alloc(g, &y.w_scatter_tc, es * (size_t)y.cin * y.np_sc));
+        DAMC_TRY(launch_pack_convt(s.weight, s.cin, s.cout, s.k, s.stride, s.pad, PK_LAST_FWD_SCATTER, 0, 1, y.cin,
+                                   y.np_sc, 1, precision, y.w_scatter_tc, stream, dirty));
       }
     }
   }
@@ -161,7 +176,8 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   ws->dz_part = (float*)take(sizeof(float) * (size_t)dz_splits_for(g, B) * B * g->nz_p);
   ws->zbuf = (float*)take(sizeof(float) * (size_t)B * g->nz);
   ws->xbuf = (float*)take(sizeof(float) * (size_t)B * g->nc * g->H * g->W);
-  ws->seed_dev = (unsigned long long*)take(16);
+  ws->xhat_buf = (float*)take(sizeof(float) * (size_t)B * g->nc * g->H * g->W);
+  ws->seed_dev = (unsigned long long*)take(32);
   ws->base = base;
   ws->bytes = o;
   return DAMC_OK;
@@ -169,7 +185,8 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
 
 static int run_gemm(const GenPack* g, const GemmPlan& p, cudaStream_t stream) {
   profile_mark(stream, true);
-  const int r = (g->use_tc && p.Wtc) ? launch_gemm_tc(p, g->precision, stream) : launch_gemm_simt(p, g->precision, stream);
+  if ((g->use_tc ? p.Wtc : p.W) == nullptr) DAMC_FAIL(DAMC_ERR_INVALID, "generator GEMM: operand layout of the active engine was not packed");
+  const int r = g->use_tc ? launch_gemm_tc(p, g->precision, stream) : launch_gemm_simt(p, g->precision, stream);
   profile_mark(stream, false);
   count_launch();
   return r;

@@ -44,6 +44,17 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, float v[4]) {
   v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
   v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
 }
+// fp32 container holding a tf32-rounded value (DAMC_PREC_TF32 storage type: rounded on store, plain fp32 on load)
+struct tf32_t { float v; };
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void load8(const tf32_t* p, float v[8]) { load8(reinterpret_cast<const float*>(p), v); }
+__device__ __forceinline__ void load4(const tf32_t* p, float v[4]) { load4(reinterpret_cast<const float*>(p), v); }
+__device__ __forceinline__ float to_f(tf32_t v) { return v.v; }
+__device__ __forceinline__ void store_t(tf32_t* p, float v) { p->v = round_tf32(v); }
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void store_t(float* p, float v) { *p = v; }

@@ -21,7 +21,7 @@
 
 namespace damc {
 
-size_t elem_size(int precision) { return is_tc_precision(precision) ? 2 : 4; }
+size_t elem_size(int precision) { return is_tc_precision(precision) ? 2 : 4; }   // fp32 and tf32 modes store fp32 containers
 
 // ---- the SIMT kernel ----------------------------------------------------------------------------------------------
 template <typename T, int BN>
@@ -149,6 +149,7 @@ static int launch_simt_t(const GemmPlan& p, cudaStream_t stream) {
 int launch_gemm_simt(const GemmPlan& p, int precision, cudaStream_t stream) {
   if (p.Cs % 16 != 0 || p.Np % 4 != 0) DAMC_FAIL(DAMC_ERR_INVALID, "SIMT GEMM needs Cs%%16==0, Np%%4==0 (Cs=%d Np=%d)", p.Cs, p.Np);
   if (precision == DAMC_PREC_FP16) return launch_simt_t<__half>(p, stream);
+  if (precision == DAMC_PREC_TF32) return launch_simt_t<tf32_t>(p, stream);   // tf32-rounded storage, fp32 FMA (cross-check engine)
   return precision == DAMC_PREC_BF16 ? launch_simt_t<__nv_bfloat16>(p, stream) : launch_simt_t<float>(p, stream);
 }
 
@@ -187,7 +188,8 @@ __device__ __forceinline__ long long pack_src_index(int mode, int cls, int t, in
 
 template <typename T>
 __global__ void pack_convt_kernel(const float* __restrict__ w, int cin, int cout, int k, int mode, int cls, int ntaps,
-                                  int Cs, int Np, int nk_layout, T* __restrict__ dst) {
+                                  int Cs, int Np, int nk_layout, T* __restrict__ dst, const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
   const long long total = (long long)ntaps * Cs * Np;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int t, c, n;
@@ -199,19 +201,22 @@ __global__ void pack_convt_kernel(const float* __restrict__ w, int cin, int cout
 }
 
 int launch_pack_convt(const float* w, int cin, int cout, int k, int stride, int pad, int mode, int cls, int ntaps,
-                      int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream) {
+                      int Cs, int Np, int nk_layout, int precision, void* dst, cudaStream_t stream, const int* dirty) {
   (void)stride; (void)pad;
   const long long total = (long long)ntaps * Cs * Np;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   if (precision == DAMC_PREC_FP16)
     pack_convt_kernel<__half><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
-                                                          reinterpret_cast<__half*>(dst));
+                                                          reinterpret_cast<__half*>(dst), dirty);
   else if (precision == DAMC_PREC_BF16)
     pack_convt_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dst));
+                                                                 reinterpret_cast<__nv_bfloat16*>(dst), dirty);
+  else if (precision == DAMC_PREC_TF32)
+    pack_convt_kernel<tf32_t><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
+                                                          reinterpret_cast<tf32_t*>(dst), dirty);
   else
     pack_convt_kernel<float><<<blocks, 256, 0, stream>>>(w, cin, cout, k, mode, cls, ntaps, Cs, Np, nk_layout,
-                                                         reinterpret_cast<float*>(dst));
+                                                         reinterpret_cast<float*>(dst), dirty);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
@@ -354,6 +359,10 @@ __global__ void __launch_bounds__(384) last_finish_kernel(const FinishArgs aa) {
     }
     T* dst = gc + (size_t)m * 64 + j * EPC;
     if constexpr (sizeof(T) == 4) {
+      if constexpr (std::is_same<T, tf32_t>::value) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vals[q] = round_tf32(vals[q]);
+      }
       *reinterpret_cast<float4*>(dst) = make_float4(vals[0], vals[1], vals[2], vals[3]);
     } else {
       uint32_t w[4];
@@ -422,6 +431,11 @@ int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, 
     if (up) return go(last_finish_kernel<__nv_bfloat16, 4, 2>);
     return go(last_finish_kernel<__nv_bfloat16, 0, 0>);
   }
+  if (precision == DAMC_PREC_TF32) {
+    if (same) return go(last_finish_kernel<tf32_t, 3, 1>);
+    if (up) return go(last_finish_kernel<tf32_t, 4, 2>);
+    return go(last_finish_kernel<tf32_t, 0, 0>);
+  }
   if (same) return go(last_finish_kernel<float, 3, 1>);
   if (up) return go(last_finish_kernel<float, 4, 2>);
   return go(last_finish_kernel<float, 0, 0>);
@@ -441,6 +455,8 @@ int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int preci
     stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<__half*>(zin), B, nz, nz_p);
   else if (precision == DAMC_PREC_BF16)
     stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<__nv_bfloat16*>(zin), B, nz, nz_p);
+  else if (precision == DAMC_PREC_TF32)
+    stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<tf32_t*>(zin), B, nz, nz_p);
   else
     stage_z_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, reinterpret_cast<float*>(zin), B, nz, nz_p);
   DAMC_CUDA(cudaGetLastError());

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <atomic>
 
 #include "damc_common.cuh"
 #include "damc_internal.h"
@@ -55,6 +56,8 @@ struct TcParams {
   const float* bias_src;   // bias vector copied into smem at kernel start (bias_floats > 0), at staging + bias_off bytes
   int bias_floats, bias_off;
   int BN, stages, b_stage_bytes;
+  int bk;           // channels per k-block = one 128-byte swizzle row: 64 (16-bit operands) or 32 (tf32: fp32 containers)
+  int tf32;         // kind::tf32 MMAs on fp32 tensors (DAMC_PREC_TF32); epilogues store tf32-rounded fp32
   int m_tiles, n_tiles, kb_per_tap, kb_total, kb_per_split;
   int Ht, Bt, tiles_per_img, tile_rows;
   uint32_t a_box_bytes, b_box_bytes, idesc;
@@ -73,11 +76,12 @@ struct RowCtx {
   int m, b, y, x;
 };
 
+template <bool F32>
 __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, int split, int n0, const uint32_t raw[16],
                                             float& loss_acc) {
   const Epilogue& e = p.epi;
   if (!r.ok || n0 >= p.Np) return;
-  if (e.kind == EPI_FWD_ACT && n0 + 16 <= p.N) {
+  if (e.kind == EPI_FWD_ACT && n0 + 16 <= p.N && !F32) {
     const long long o = (long long)r.b * e.o_b + (long long)(r.y * e.sy + e.py) * e.o_y +
                         (long long)(r.x * e.sx + e.px) * e.o_x + n0;
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (n0 % e.bias_mod));
@@ -97,7 +101,7 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     return;
   }
-  if (e.kind == EPI_DGRAD_MASK && n0 + 16 <= p.N) {
+  if (e.kind == EPI_DGRAD_MASK && n0 + 16 <= p.N && !F32) {
     const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.act) + (long long)r.m * p.N + n0);
     long long o;
     if (e.planar_out) {
@@ -147,7 +151,8 @@ __device__ __forceinline__ void epi_chunk16(const GemmPlan& p, const RowCtx& r, 
 #pragma unroll 1
   for (int j = 0; j < 16; ++j)
     if (n0 + j < p.N) {
-      if (p.op_fp16) epilogue_elem<__half>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+      if (F32) epilogue_elem<tf32_t>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
+      else if (p.op_fp16) epilogue_elem<__half>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
       else epilogue_elem<__nv_bfloat16>(p, split, r.m, r.b, r.y, r.x, n0 + j, __uint_as_float(raw[j]), loss_acc);
     }
 }
@@ -168,12 +173,12 @@ struct StagedEpi {
   __device__ __forceinline__ static unsigned long long act_ptr_bits(const GemmPlan& p, const RowCtx& rc) {
     return (unsigned long long)(reinterpret_cast<const __nv_bfloat16*>(p.epi.act) + (rc.ok ? (long long)rc.m * p.N : 0ll));
   }
+  template <bool F32>
   __device__ __forceinline__ void set_out(const GemmPlan& p, const RowCtx& rc, int cls) {
     const Epilogue& e = p.epi;
-    __nv_bfloat16* out_row = nullptr;
+    long long o = 0;   // element offset of this lane's output row
     if (rc.ok) {
       if (e.kind == EPI_DGRAD_MASK) {
-        long long o;
         if (e.planar_out) {
           const int Hh = p.Hm >> 1, Wh = p.Wm >> 1;
           o = (long long)((rc.y & 1) * 2 + (rc.x & 1)) * p.B * Hh * Wh * p.N +
@@ -181,18 +186,15 @@ struct StagedEpi {
         } else {
           o = (long long)rc.m * p.N;
         }
-        out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
       } else {
         const int py = p.ncls > 1 ? (cls >> 1) : e.py, px = p.ncls > 1 ? (cls & 1) : e.px;
-        out_row = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)rc.b * e.o_b +
-                  (long long)(rc.y * e.sy + py) * e.o_y + (long long)(rc.x * e.sx + px) * e.o_x;
+        o = (long long)rc.b * e.o_b + (long long)(rc.y * e.sy + py) * e.o_y + (long long)(rc.x * e.sx + px) * e.o_x;
       }
     }
-    out_bits = (unsigned long long)out_row;
+    out_bits = rc.ok ? (unsigned long long)e.out + (unsigned long long)o * (F32 ? 4ull : 2ull) : 0ull;
     mrow_bits = 0ull;
     if (e.maskbits != nullptr && rc.ok) {
-      const long long elem0 = e.kind == EPI_DGRAD_MASK ? (long long)rc.m * p.N
-                                                       : (long long)(out_row - reinterpret_cast<__nv_bfloat16*>(e.out));
+      const long long elem0 = e.kind == EPI_DGRAD_MASK ? (long long)rc.m * p.N : o;
       mrow_bits = (unsigned long long)(e.maskbits + (elem0 >> 5));
     }
   }
@@ -221,6 +223,7 @@ struct StagedEpi {
     __syncwarp();
   }
   // accumulators of one segment -> epilogue math -> smem -> global
+  template <bool F32>
   __device__ __forceinline__ void process(const GemmPlan& p, uint32_t t_seg, uint32_t my_stage, int lane, int n_base,
                                           uint2 mw, const float* sbias /* smem bias + (n_base % bias_mod) */) const {
     const Epilogue& e = p.epi;
@@ -241,6 +244,32 @@ struct StagedEpi {
         const int jj = (c >> 3) + g;
         const uint32_t addr = my_stage + (uint32_t)lane * row_bytes + (uint32_t)((jj ^ (lane & (CPR - 1))) << 4);
         uint32_t w[4];
+        if constexpr (F32) {
+          // tf32 mode: 8 columns = 32 bytes of this lane's fp32 row, rounded to tf32 (the next GEMM's operand) -> one 256-bit store
+          uint32_t f[8];
+          if (is_mask) {
+#pragma unroll
+            for (int t2 = 0; t2 < 8; ++t2)
+              f[t2] = __float_as_uint(tf32_rna(__uint_as_float(v[8 * g + t2]) * ((mword & (1u << (8 * g + t2))) ? 1.f : e.slope)));
+          } else {
+            const float4* bp = reinterpret_cast<const float4*>(sbias + c + 8 * g);
+            const float4 b0v = bp[0], b1v = bp[1];
+            const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+            for (int t2 = 0; t2 < 8; ++t2) {
+              const float h0 = __uint_as_float(v[8 * g + t2]) + bb[t2];
+              const bool p0 = h0 > 0.f;
+              oword |= (p0 ? 1u : 0u) << (8 * g + t2);
+              f[t2] = __float_as_uint(tf32_rna(p0 ? h0 : h0 * e.slope));
+            }
+          }
+          if (out_bits && !(dbg & 1)) {
+            const unsigned long long a = out_bits + 4ull * (unsigned long long)(n_base + c + 8 * g);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(f[0]), "r"(f[1]), "r"(f[2]),
+                         "r"(f[3]), "r"(f[4]), "r"(f[5]), "r"(f[6]), "r"(f[7]) : "memory");
+          }
+          continue;
+        }
         if (is_mask && bits) {
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
@@ -328,7 +357,9 @@ __device__ __forceinline__ Tap up_fwd_tap(int cls, int t) {
 // CG = CTAs per MMA: 1, or 2 (cta_group::2: a CTA pair computes a 256 x 256 tile; each CTA stages its own 128 rows of
 // A and 128 of the 256 weight rows, so L2->smem traffic and B smem reads per FLOP drop by a third; the leader CTA's
 // MMA thread issues for both, commits multicast to both CTAs' barriers).
-template <int EW, int CG>
+// F32 = tf32 mode (fp32 containers, kind::tf32 MMAs, fp32 row stores); a template parameter so that the 16-bit
+// instantiations keep their register allocation.
+template <int EW, int CG, bool F32>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ TcParams P) {
@@ -415,7 +446,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int kb0 = ncls > 1 ? 0 : sp * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
         const int wrow0 = cls * p.ntaps * p.Np;  // class block inside the weight tensor
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int t = kb / P.kb_per_tap, c0 = (kb - t * P.kb_per_tap) * TC_BK;
+          const int t = kb / P.kb_per_tap, c0 = (kb - t * P.kb_per_tap) * P.bk;
           const Tap tp = ncls > 1 ? up_fwd_tap(cls, t) : p.taps[t];
           mbar_wait(bar_empty(stage), phase ^ 1u);
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
@@ -461,9 +492,15 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t d_blk = den_kind ? d_tmem + (uint32_t)(kb < P.den_kb_h ? P.BN / 2 : 0) : d_tmem;
           const bool first_kb = den_kind ? (kb == kb0 || kb == P.den_kb_h) : kb == kb0;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {  // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
-            if (CG == 2) umma_bf16_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (!first_kb || k > 0) ? 1u : 0u);
-            else umma_bf16(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (!first_kb || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {  // +32 bytes (16 bf16 | 8 tf32) along K inside the 128-byte swizzle row
+            const uint32_t acc = (!first_kb || k > 0) ? 1u : 0u;
+            if (F32) {
+              if (CG == 2) umma_tf32_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
+              else umma_tf32(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
+            } else {
+              if (CG == 2) umma_bf16_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
+              else umma_bf16(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
+            }
           }
           if (CG == 2) umma_commit_2sm(bar_empty(stage)); else umma_commit(bar_empty(stage));  // frees the smem slot
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
@@ -550,7 +587,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int as = k & 1;
           if (sg == 0) {
             const RowCtx rc = row_ctx(unit + k * nunits, nt, sp);
-            se.set_out(p, rc, sp);
+            se.template set_out<F32>(p, rc, sp);
           }
           const int seg = (grp + NG * sg) * 64, n_base = nt * P.BN + seg;
           uint2 mw = make_uint2(0u, 0u);
@@ -566,7 +603,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (n_base < p.N) {
             int bq, brem = 0;
             if (!is_mask) P.fd_bias.divmod(n_base, bq, brem);
-            se.process(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base, mw,
+            se.template process<F32>(p, t_lane + (uint32_t)as * 256u + (uint32_t)seg, my_stage, lane, n_base, mw,
                        (P.bias_floats ? den_bias : p.epi.bias) + brem);
           }
           if (sg == nseg_w - 1) {
@@ -658,12 +695,12 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (c + 32 <= P.BN) {
             tmem_ld32(t_row + (uint32_t)c, v);
             tmem_ld_wait();
-            epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
-            epi_chunk16(p, rc, sp, nt * P.BN + c + 16, v + 16, loss_acc);
+            epi_chunk16<F32>(p, rc, sp, nt * P.BN + c, v, loss_acc);
+            epi_chunk16<F32>(p, rc, sp, nt * P.BN + c + 16, v + 16, loss_acc);
           } else {
             tmem_ld16(t_row + (uint32_t)c, v);
             tmem_ld_wait();
-            epi_chunk16(p, rc, sp, nt * P.BN + c, v, loss_acc);
+            epi_chunk16<F32>(p, rc, sp, nt * P.BN + c, v, loss_acc);
           }
         }
         tc_fence_before();
@@ -756,7 +793,10 @@ struct TcLaunch {
 static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   EncodeTiledFn enc = get_encode();
   if (!enc) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  if (p.Cs % TC_BK) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, TC_BK);
+  const bool f32 = precision == DAMC_PREC_TF32;
+  const int bk = f32 ? TC_BK / 2 : TC_BK;          // elements per 128-byte swizzle row
+  const cuuint64_t esz = f32 ? 4 : 2;
+  if (p.Cs % bk) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: K per tap (%d) must be a multiple of %d", p.Cs, bk);
   if (p.Np % 16) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: padded N (%d) must be a multiple of 16", p.Np);
   if (p.Wm > TC_BM) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: pixel-grid width %d > %d", p.Wm, TC_BM);
   if (p.ncls > 1 && (p.ncls != 4 || p.ntaps != 4 || p.ksplit != 1 || p.epi.kind != EPI_FWD_ACT || p.Np % 64))
@@ -766,9 +806,15 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.plan = p;
   const bool fp16 = precision == DAMC_PREC_FP16;
   P.plan.op_fp16 = fp16 ? 1 : 0;
-  const CUtensorMapDataType tm_dtype = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  P.plan.op_f32 = f32 ? 1 : 0;
+  P.bk = bk;
+  P.tf32 = f32 ? 1 : 0;
+  const CUtensorMapDataType tm_dtype = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   P.BN = p.Np < 256 ? p.Np : 256;
   const bool den_kind = p.epi.kind == EPI_DEN_LAYER || p.epi.kind == EPI_DEN_FINAL;
+  if (f32 && (den_kind || (p.epi.kind == EPI_DGRAD_MASK && p.epi.maskbits == nullptr)))
+    DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: the tf32 mode covers the generator GEMMs with 1-bit masks only");
   if (den_kind) {
     P.BN = tc_den_tile_width(p.B, p.Np);
     if (p.epi.den.bn != P.BN) DAMC_FAIL(DAMC_ERR_INVALID, "tcgen05 GEMM: denoiser weights packed for tile width %d, launch uses %d", p.epi.den.bn, P.BN);
@@ -791,7 +837,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   auto log2_or_neg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
   P.wm_shift = log2_or_neg(p.Wm);
   P.per_img_shift = log2_or_neg(P.Ht * p.Wm);
-  P.kb_per_tap = p.Cs / TC_BK;
+  P.kb_per_tap = p.Cs / bk;
   P.kb_total = p.ntaps * P.kb_per_tap;
   P.kb_per_split = ceil_div(P.kb_total, p.ksplit);
   if ((long long)P.kb_per_split * (p.ksplit - 1) >= P.kb_total)
@@ -801,8 +847,8 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.fd_tpi = make_fastdiv(P.tiles_per_img);
   P.fd_perimg = make_fastdiv(P.Ht * p.Wm);
   P.fd_wm = make_fastdiv(p.Wm);
-  P.a_box_bytes = (uint32_t)P.tile_rows * TC_BK * 2;
-  P.b_box_bytes = (uint32_t)P.BN * TC_BK * 2;
+  P.a_box_bytes = (uint32_t)P.tile_rows * 128u;   // one 128-byte swizzle row per pixel / weight row
+  P.b_box_bytes = (uint32_t)P.BN * 128u;
   P.stage_cols = 0;
   P.cls_inner = getenv("DAMC_TC_CLS_OUTER") ? 0 : 1;
   P.dbg = getenv("DAMC_TC_DBG") ? atoi(getenv("DAMC_TC_DBG")) : 0;
@@ -845,7 +891,7 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   P.stages = stages_for(staging_bytes);
   if (P.stages < 2) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: not enough shared memory for a pipeline (BN=%d)", P.BN);
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  const uint32_t opfmt = fp16 ? 0u : 1u;  // kind::f16 operand format: 0 = f16, 1 = bf16
+  const uint32_t opfmt = f32 ? 2u : fp16 ? 0u : 1u;  // operand format: 0 = f16, 1 = bf16 (kind::f16); 2 = tf32 (kind::tf32)
   const int mma_n = den_kind ? P.BN / 2 : P.BN;
   P.idesc = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
 
@@ -854,10 +900,10 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   {
     const int nplanes = [&] { int mx = 0; for (int t = 0; t < p.ntaps; ++t) mx = std::max(mx, (int)p.taps[t].plane); return mx + 1; }();
     const cuuint64_t dims[5] = {(cuuint64_t)p.Cs, (cuuint64_t)p.Wm, (cuuint64_t)p.Hm, (cuuint64_t)p.B, (cuuint64_t)nplanes};
-    const cuuint64_t row = (cuuint64_t)p.Cs * 2;
-    const cuuint64_t plane_bytes = nplanes > 1 ? (cuuint64_t)p.plane_stride * 2 : row * p.Wm * p.Hm * p.B;
+    const cuuint64_t row = (cuuint64_t)p.Cs * esz;
+    const cuuint64_t plane_bytes = nplanes > 1 ? (cuuint64_t)p.plane_stride * esz : row * p.Wm * p.Hm * p.B;
     const cuuint64_t strides[4] = {row, row * p.Wm, row * p.Wm * p.Hm, plane_bytes};
-    const cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)p.Wm, (cuuint32_t)P.Ht, (cuuint32_t)P.Bt, 1};
+    const cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)p.Wm, (cuuint32_t)P.Ht, (cuuint32_t)P.Bt, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = enc(&tmA, tm_dtype, 5, const_cast<void*>(p.A), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -866,8 +912,8 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)p.Cs, (cuuint64_t)(p.ncls > 1 ? p.ncls : 1) * p.ntaps * p.Np};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(den_kind ? P.BN / 2 : P.BN / cg)};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.Cs * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(den_kind ? P.BN / 2 : P.BN / cg)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&tmB, tm_dtype, 2, const_cast<void*>(p.Wtc), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -885,18 +931,24 @@ int tc_launch(TcLaunch* L, cudaStream_t stream) {
   const GemmPlan& p = P.plan;
   const size_t smem = L->smem;
   const int ew = L->ew, cg = L->cg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  static int num_sms = 0;
+  // per-device launch state: the dynamic-smem opt-in is a per-device function attribute and the persistent grid is sized
+  // from the device's own SM count (one process may drive several GPUs; MCMC.py picks the device per tensor)
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> sms_of[kMaxDev];
+  int dev = 0;
+  DAMC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "tcgen05 GEMM: device ordinal %d out of range", dev);
+  int num_sms = sms_of[dev].load(std::memory_order_acquire);
   if (!num_sms) {
-    int dev = 0;
-    DAMC_CUDA(cudaGetDevice(&dev));
+    const int big = 227 * 1024;
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    DAMC_CUDA(cudaFuncSetAttribute(convgemm_tc_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     DAMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    sms_of[dev].store(num_sms, std::memory_order_release);   // idempotent: a racing thread repeats the same calls
   }
   static const bool use_pdl = []{ const char* e = getenv("DAMC_TC_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg{};
@@ -918,15 +970,21 @@ int tc_launch(TcLaunch* L, cudaStream_t stream) {
     attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
     cfg.numAttrs = na;
-    DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2>, L->tmA, L->tmB, L->P));
+    if (P.tf32) DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2, true>, L->tmA, L->tmB, L->P));
+    else DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 2, false>, L->tmA, L->tmB, L->P));
     return DAMC_OK;
   }
   const int total = P.m_tiles * P.n_tiles * p.ksplit * (p.ncls > 1 ? p.ncls : 1);
   cfg.gridDim = dim3(std::min(total, num_sms));
   cfg.blockDim = dim3(64 + 32 * ew);
   cfg.numAttrs = na;
-  if (ew == 16) DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<16, 1>, L->tmA, L->tmB, L->P));
-  else DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 1>, L->tmA, L->tmB, L->P));
+  if (P.tf32) {
+    if (ew == 16) DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<16, 1, true>, L->tmA, L->tmB, L->P));
+    else DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 1, true>, L->tmA, L->tmB, L->P));
+  } else {
+    if (ew == 16) DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<16, 1, false>, L->tmA, L->tmB, L->P));
+    else DAMC_CUDA(cudaLaunchKernelEx(&cfg, convgemm_tc_kernel<8, 1, false>, L->tmA, L->tmB, L->P));
+  }
   return DAMC_OK;
 }
 

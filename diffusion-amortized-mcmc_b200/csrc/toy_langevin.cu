@@ -17,7 +17,8 @@ struct ToyPack : damc_handle {
   const float* src[8] = {};
   size_t sizes[8] = {};
   ~ToyPack() override { if (slab) cudaFree(slab); }
-  int refill(cudaStream_t stream) override {
+  int refill(cudaStream_t stream, const int* dirty) override {
+    (void)dirty;   // tiny MLP: always copied
     float* p = slab;
     for (int i = 0; i < 8; ++i) {
       DAMC_CUDA(cudaMemcpyAsync(p, src[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -258,7 +259,7 @@ extern "C" int damc_pack_toy_mlp(damc_handle** out, int nz, int nh, int nx, cons
     t->src[2 * i] = host_W[i]; t->src[2 * i + 1] = host_b[i];
     t->sizes[2 * i] = sizes[2 * i]; t->sizes[2 * i + 1] = sizes[2 * i + 1];
   }
-  const int r = t->refill((cudaStream_t)stream);
+  const int r = t->refill((cudaStream_t)stream, nullptr);
   if (r != DAMC_OK) { delete t; return r; }
   *out = t;
   return DAMC_OK;

@@ -22,14 +22,18 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check
 
-_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
-DEFAULT_PRECISION = "fp32"
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16, "tf32": _lib.PREC_TF32}
+_DEN_PRECISIONS = {k: v for k, v in _PRECISIONS.items() if k != "tf32"}   # denoiser / encoder GEMMs: no tf32 variant
+# 'tf32' is what the unmodified reference computes on a GPU: torch runs its (transposed) convolutions on the tensor cores
+# in TF32 by default (torch.backends.cudnn.allow_tf32 = True; reference src/MCMC.py:55-60 goes through cuDNN).
+DEFAULT_PRECISION = "tf32"
 DEFAULT_DENOISER_PRECISION = "fp32"
 
 
 def set_default_precision(name):
-    """'fp32' (CUDA-core fp32 GEMMs, rel 1e-3 parity), 'bf16' (tcgen05 tensor cores, rel 2e-2) or 'fp16' (same
-    tensor-core engine with fp16 operands: ~8x smaller operand rounding at the same speed)."""
+    """Generator GEMM arithmetic: 'tf32' (default: tcgen05 tensor cores on tf32-rounded fp32 tensors, rel 1e-3 parity),
+    'bf16' (tcgen05, 16-bit operands, rel 2e-2, 2x the tf32 throughput), 'fp16' (same engine as bf16 with fp16 operands:
+    ~8x smaller operand rounding at the same speed) or 'fp32' (CUDA-core fp32 FMA GEMMs: exact-fp32 cross-check)."""
     global DEFAULT_PRECISION
     if name not in _PRECISIONS:
         raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
@@ -40,8 +44,8 @@ def set_default_denoiser_precision(name):
     """Arithmetic of the DAMC denoiser GEMMs: 'fp32' (one persistent CUDA-core kernel for all T steps; parity mode) or
     'bf16' / 'fp16' (per-layer tcgen05 GEMMs; the throughput mode for large batches of chains)."""
     global DEFAULT_DENOISER_PRECISION
-    if name not in _PRECISIONS:
-        raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
+    if name not in _DEN_PRECISIONS:
+        raise ValueError(f"precision must be one of {list(_DEN_PRECISIONS)}")
     DEFAULT_DENOISER_PRECISION = name
 
 
@@ -265,8 +269,9 @@ def sample_langevin_post_z_with_prior(z, x, netG, netE, g_l_steps, g_llhd_sigma,
     keep, nptr = _noise_ptr(noise, (K, B, nz), zd.device)
     trace = torch.empty(K, 4, dtype=torch.float32, device=zd.device) if verbose and K > 0 else None
     if x_hat_out is not None:
-        if x_hat_out.shape != xs.shape or x_hat_out.dtype != torch.float32 or not x_hat_out.is_contiguous():
-            raise RuntimeError("x_hat_out must be a contiguous float32 tensor shaped like x")
+        if x_hat_out.shape != xs.shape or x_hat_out.dtype != torch.float32 or not x_hat_out.is_contiguous() or \
+                x_hat_out.device != zd.device:
+            raise RuntimeError(f"x_hat_out must be a contiguous float32 tensor shaped like x on {zd.device}")
     nbytes = lib().damc_generator_workspace_bytes(gh.ptr, B)
     ws = _workspace(zd.device, nbytes)
     with torch.cuda.device(zd.device):
@@ -288,12 +293,31 @@ def sample_langevin_post_z_with_prior(z, x, netG, netE, g_l_steps, g_llhd_sigma,
     return z.detach()
 
 
+def _den_prec(precision):
+    name = precision or DEFAULT_DENOISER_PRECISION
+    if name not in _DEN_PRECISIONS:
+        raise ValueError(f"denoiser / encoder precision must be one of {list(_DEN_PRECISIONS)} (got {name!r})")
+    return name
+
+
+def _check_rows(t, what, rows, cols, device=None):
+    """Raise (like the reference's matmul / reshape would) instead of letting a kernel run past a mis-shaped buffer."""
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != cols:
+        raise RuntimeError(f"{what} must have shape [{rows}, {cols}], got {tuple(t.shape)}")
+    if device is not None:
+        device = torch.device(device)
+        if t.device.type != device.type or (device.index is not None and t.device.index != device.index):
+            raise RuntimeError(f"{what} is on {t.device}, expected {device}")
+
+
 def generator_forward(netG, z, precision=None):
     """x_hat = netG(z) through the packed kernels (no autograd graph)."""
     zd = _f32_cuda(z, "z")
     gh = pack_generator(netG, precision)
     nz, nc, H, W = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     check(lib().damc_generator_shape(gh.ptr, C.byref(nz), C.byref(nc), C.byref(H), C.byref(W)))
+    if zd.dim() != 2 or zd.shape[1] != nz.value:
+        raise RuntimeError(f"z must have shape [B, {nz.value}] for this generator, got {tuple(zd.shape)}")
     B = zd.shape[0]
     out = torch.empty(B, nc.value, H.value, W.value, dtype=torch.float32, device=zd.device)
     nbytes = lib().damc_generator_workspace_bytes(gh.ptr, B)
@@ -446,7 +470,7 @@ def encoder_forward(enc, x, precision=None):
     """xemb = enc(x) [B, nemb] through libdamc_b200: direct first convolution, k4-s2-p1 convolutions as the generator
     engines' stride-2 GEMMs (tcgen05 for 'bf16' / 'fp16', CUDA-core for 'fp32'), fused InstanceNorm + LeakyReLU kernels.
     Raises for encoders outside that family (e.g. the 28x28 MNIST encoder, odd-sized maps)."""
-    precision = precision or DEFAULT_DENOISER_PRECISION
+    precision = _den_prec(precision)
     xs = _f32_cuda(x, "x")
     if xs.dim() != 4:
         raise RuntimeError("x must be [B, nc, H, W]")
@@ -498,7 +522,7 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
     noise: optional [T-1,b,nz] injected normals; z_init: optional z_T (otherwise torch.randn as the reference)."""
     if x is not None and cond_w is not None and cond_w > 0:
         raise NotImplementedError("classifier-free guidance (cond_w > 0) is never taken by the reference's callers")
-    prec = _PRECISIONS[precision or DEFAULT_DENOISER_PRECISION]
+    prec = _PRECISIONS[_den_prec(precision)]
     with torch.no_grad():
         if xemb is not None:  # precomputed context embedding (skips the encoder / prior_emb)
             b, device = len(xemb), xemb.device
@@ -519,6 +543,8 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
         raise RuntimeError("damc_sample needs a CUDA device (damc_b200 has no CPU fallback)")
     xemb = _f32_cuda(xemb, "xemb")
     zt = _f32_cuda(zt, "z_T")
+    _check_rows(xemb, "xemb", b, int(Q.nxemb), device)
+    _check_rows(zt, "z_T", b, int(Q.nz), device)
     T = int(Q.n_interval)
     h = pack_denoiser(Q)
     keep, nptr = _noise_ptr(noise, (T - 1, b, Q.nz), device)
@@ -538,7 +564,11 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
 def denoiser_eps(Q, z, logsnr, xemb, *, precision=None):
     """One eps-prediction Q.p(z, logsnr, xemb) with a batch-constant logsnr (float) through the CUDA library."""
     zd, xe = _f32_cuda(z, "z"), _f32_cuda(xemb, "xemb")
-    prec = _PRECISIONS[precision or DEFAULT_DENOISER_PRECISION]
+    prec = _PRECISIONS[_den_prec(precision)]
+    if zd.dim() != 2:
+        raise RuntimeError(f"z must be [B, {int(Q.nz)}], got {tuple(zd.shape)}")
+    _check_rows(zd, "z", zd.shape[0], int(Q.nz))
+    _check_rows(xe, "xemb", zd.shape[0], int(Q.nxemb), zd.device)
     h = pack_denoiser(Q)
     out = torch.empty_like(zd)
     nbytes = lib().damc_denoise_workspace_bytes(h.ptr, zd.shape[0], 1, prec)

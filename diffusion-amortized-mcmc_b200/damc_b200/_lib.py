@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdamc_b200.so")
 
 OK = 0
-PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_TF32 = 0, 1, 2, 3
 
 
 class ConvTLayer(C.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
     "damc_encoder_forward": (_I, [_P, _P, _P, _I, _P, _SZ, _P]),
     "damc_selftest": (_I, []),
     "damc_launch_count": (C.c_longlong, []),
+    "damc_graph_replays": (C.c_longlong, [_P]),
     "damc_profile_enable": (_I, [_I]),
     "damc_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }

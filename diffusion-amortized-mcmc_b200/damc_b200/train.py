@@ -28,7 +28,7 @@ class TrainConfig:  # defaults = train_gen_recon.py:383-402
     p_mask: float = 0.2
     q_updates: int = 6
     max_norm: float = 100.0
-    precision: str = "fp32"
+    precision: str = "tf32"   # what the reference's cuDNN convolutions compute in by default on a GPU
 
 
 def _step(loss, params, opt, cfg, group):
@@ -40,9 +40,14 @@ def _step(loss, params, opt, cfg, group):
     opt.step()
 
 
-def training_iteration(x, G, E, Q, Q_dummy, G_opt, E_opt, Q_opt, cfg=TrainConfig(), group=None, chain0=0):
-    """x: this rank's image shard [B,nc,H,W] on its GPU.  Returns dict of detached scalar losses."""
+def training_iteration(x, G, E, Q, Q_dummy, G_opt, E_opt, Q_opt, cfg=TrainConfig(), group=None, chain0=None):
+    """x: this rank's image shard [B,nc,H,W] on its GPU.  Returns dict of detached scalar losses.
+    chain0: global index of this shard's first chain (Philox key).  Default: rank * B under torch.distributed -- the
+    reference seeds every process alike (torch.manual_seed(args.seed), train_gen_recon.py:353), so without the offset all
+    ranks would draw the same seed AND the same chain indices, i.e. identical Langevin noise on every shard."""
     B = x.size(0)
+    if chain0 is None:
+        chain0 = dist.get_rank(group) * B if (dist.is_available() and dist.is_initialized()) else 0
     z_mask = (torch.rand(B, device=x.device) >= cfg.p_mask).float().unsqueeze(-1)
     Q.eval(); G.eval(); E.eval()
     with torch.no_grad():

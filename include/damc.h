@@ -34,10 +34,13 @@ enum { DAMC_OK = 0, DAMC_ERR_INVALID = 1, DAMC_ERR_UNSUPPORTED = 2, DAMC_ERR_CUD
 /* arithmetic of the GEMM operands -- generator (chosen at pack time) and DAMC denoiser (chosen per call).  The EBM, the
  * Langevin / reverse-step updates, z itself and every accumulator are always fp32. */
 enum {
-  DAMC_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM: the rel-1e-3 parity mode                      */
+  DAMC_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM: exact fp32 FMA accumulation (cross-check mode)     */
   DAMC_PREC_BF16 = 1, /* bf16 operands, fp32 accumulate on tcgen05/TMEM fed by TMA: the throughput mode */
-  DAMC_PREC_FP16 = 2  /* same engine with fp16 operands (8x finer operand rounding than bf16, same speed); the
+  DAMC_PREC_FP16 = 2, /* same engine with fp16 operands (8x finer operand rounding than bf16, same speed); the
                          gradient chain is carried scaled by sigma^2 so that it stays inside the fp16 range */
+  DAMC_PREC_TF32 = 3  /* generator only: the same tcgen05 engine with fp32 tensors rounded to tf32 (10-bit mantissa,
+                         fp32 range) and kind::tf32 MMAs -- the arithmetic torch/cuDNN use by default for the reference's
+                         convolutions on a GPU (src/MCMC.py:55-60); the rel-1e-3 parity mode and the library default */
 };
 
 int damc_version(void);
@@ -158,6 +161,8 @@ int damc_encoder_forward(const damc_handle* enc, const float* x, float* xemb, in
 /* damc_selftest : host-only consistency checks of the library's index arithmetic (no GPU needed); 0 = ok. */
 int damc_selftest(void);
 long long damc_launch_count(void);
+/* number of posterior calls on this generator handle served by replaying a captured CUDA graph (-1: not a generator) */
+long long damc_graph_replays(const damc_handle* gen);
 int damc_profile_enable(int on);
 int damc_profile_collect(double* gemm_ms, long long* gemm_launches);
 

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = {"fp32": 1e-3, "bf16": 2e-2, "fp16": 4e-3}
+TOL = {"fp32": 1e-3, "tf32": 1e-3, "bf16": 2e-2, "fp16": 4e-3}
 
 
 def relmax(a, b):
@@ -110,11 +110,16 @@ def test_prior_langevin_golden(name, dev):
         assert abs(float(a[2]) - float(b[2])) <= 2e-3 * max(1.0, abs(float(b[2])))
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("name", _names("post_"))
-def test_posterior_langevin_fp32_golden(name, dev):
+def test_posterior_langevin_fp32_golden(name, prec, dev):
+    """The rel-1e-3 modes against the reference's fp64 run: 'fp32' (CUDA-core FMA GEMMs) on every golden, 'tf32' (the
+    default: tcgen05 kind::tf32 on tf32-rounded fp32 tensors) on every golden at tensor-core granularity (ngf >= 64)."""
     from damc_b200 import MCMC
     g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
     nz, ngf, nc, B, K = (int(v) for v in g["cfg"])
+    if prec == "tf32" and ngf < 64:
+        pytest.skip("the tensor-core engine needs channel counts that are multiples of 64")
     sigma, step, noise_on = float(g["sigma"]), float(g["step"]), bool(g["noise_on"])
     layers = synth.gen_layers(str(g["dataset"]), nz, ngf, nc)
     gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, gain=float(g["gain"]))
@@ -123,15 +128,17 @@ def test_posterior_langevin_fp32_golden(name, dev):
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, step, True,
-                                                     noise=noise.to(dev), precision="fp32")
+                                                     noise=noise.to(dev), precision=prec)
     ref_drift = relmax(g["z_f32"], g["z_f64"])
-    assert_z_close(out, g, TOL["fp32"], name)
+    assert_z_close(out, g, TOL[prec], name + f"[{prec}]")
     assert out.data_ptr() == z.data_ptr()
     assert all(p.requires_grad for p in list(G.parameters()) + list(E.parameters()))
     # G(z_K) crop and the verbose trace agree with the reference
-    xh = MCMC.generator_forward(G, out, precision="fp32")[:, :, :4, :4]
+    xh = MCMC.generator_forward(G, out, precision=prec)[:, :, :4, :4]
     gen64 = synth.gen_list_from_state(gsd, layers, torch.float64)
-    assert relmax(xh, O.gen_forward(gen64, out.cpu().double())[:, :, :4, :4]) < 1e-4  # G at OUR z_K (flip-independent)
+    e_xh = relmax(xh, O.gen_forward(gen64, out.cpu().double())[:, :, :4, :4])   # G at OUR z_K (flip-independent)
+    print(f"{name}[{prec}]: G(z_K) crop err {e_xh:.3e}")
+    assert e_xh < (1e-4 if prec == "fp32" else 3e-3)
     ours, theirs = buf.getvalue().strip().split("\n"), str(g["log_f64"]).strip().split("\n")
     assert ours[0] == theirs[0] == "Log posterior sampling."
     to = [t.split("/") for t in ours[1].replace("Step/cross_entropy/recons_loss: ", "").split()]
@@ -143,7 +150,7 @@ def test_posterior_langevin_fp32_golden(name, dev):
 
 
 BF16_CASES = ["post_cifar10_full_k5", "post_svhn_full_k5", "post_cifar10_full", "post_svhn_full", "post_mnist_full",
-              "post_celebaHQ_w64"]
+              "post_celebaHQ_w64", "post_celebaHQ_full", "post_celebaHQ_full_g85_k2"]
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
@@ -163,7 +170,8 @@ def test_posterior_langevin_bf16_golden(name, prec, dev):
     assert_z_close(out, g, TOL[prec], name + f"[{prec}]")
 
 
-@pytest.mark.parametrize("prec,tol_med,tol_max", [("fp32", 2e-5, 5e-3), ("bf16", 4e-2, 8e-2), ("fp16", 1.2e-2, 3e-2)])
+@pytest.mark.parametrize("prec,tol_med,tol_max", [("fp32", 2e-5, 5e-3), ("bf16", 4e-2, 8e-2), ("fp16", 1.2e-2, 3e-2),
+                                                  ("tf32", 1.2e-2, 3e-2)])
 @pytest.mark.parametrize("dataset,nz,ngf,nc", [("cifar10", 128, 128, 3), ("svhn", 100, 64, 3), ("mnist", 8, 128, 1)])
 def test_single_step_gradient_trained_like_weights(dataset, nz, ngf, nc, prec, tol_med, tol_max, dev):
     """One noise-free step at full width with O(1) pre-activations (gain 0.85): dU/dz recovered from the update must
@@ -409,7 +417,9 @@ def test_damc_graph_replay_matches_direct_launches(dev):
     (z staged through the workspace, Philox seed read from device memory).  Direct launches (call 1), the capturing call
     (2) and replays (3+) must agree bit for bit; a new seed on a replay must give new noise, equal to a direct run's."""
     from damc_b200 import MCMC, diffusion_net as dn
-    T, nz, B = 16, 128, 96
+    # B > 8 x 128: the one-launch cluster kernel does not take the batch, so the per-layer launches -- the path that is
+    # captured into a graph (denoiser_tc.cu) -- run.  (Up to 1 024 chains den_cluster_run returns before the graph code.)
+    T, nz, B = 16, 128, 1100
     Q = dn._netQ_U(nc=3, nz=nz, nxemb=1024, ntemb=128, nif=64, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
                    logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10")
     Q.load_state_dict(synth.module_state_like(Q, prefix="Q."))
