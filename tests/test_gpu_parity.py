@@ -38,14 +38,14 @@ def chain_errs(a, b):
     return np.abs(a - b).max(axis=1) / (np.abs(b).max(axis=1) + 1e-30)
 
 
-def assert_z_close(out, g, tol, name):
+def assert_z_close(out, g, tol, name, extra_drift=0.0):
     """K-step parity bound.  Well-conditioned cases (default-init weight profile, gain 0): every chain within
     max(tol, 2 x reference drift).  Trained-like weights (gain > 0): the smooth dynamics contract (a 1e-6 perturbation
     shrinks), but one LeakyReLU kink flip -- a pre-activation within fp32 rounding of zero, resolved differently by two
     correct implementations -- moves that chain by ~1e-2 (measured on the fp64 oracle, tools/ and DESIGN.md); so there
     the bound applies to the median chain and to >= 60% of the chains, with a loose sanity bound on the rest."""
     ref_drift = relmax(g["z_f32"], g["z_f64"])
-    bound = max(tol, 2 * ref_drift)
+    bound = max(tol, 2 * ref_drift, 2 * extra_drift)
     per = chain_errs(out, g["z_f64"])
     print(f"{name}: per-chain err median {np.median(per):.3e} max {per.max():.3e}   reference fp32-vs-fp64 {ref_drift:.3e}")
     if float(g["gain"]) == 0.0 or len(per) < 3:
@@ -129,8 +129,24 @@ def test_posterior_langevin_fp32_golden(name, prec, dev):
     with contextlib.redirect_stdout(buf):
         out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, step, True,
                                                      noise=noise.to(dev), precision=prec)
-    ref_drift = relmax(g["z_f32"], g["z_f64"])
-    assert_z_close(out, g, TOL[prec], name + f"[{prec}]")
+    tf32_drift = 0.0
+    if prec == "tf32" and float(g["gain"]) > 0.0:
+        # Trained-like weights at sigma = 0.1: x_hat's operand rounding (2^-11) is amplified by 1/sigma^2 against a
+        # residual of O(sigma), so ANY single-pass TF32 evaluation of dU/dz is ~1e-2 off -- including the reference's
+        # own, which runs these convolutions in TF32 on a GPU by default (torch.backends.cudnn.allow_tf32; reference
+        # src/MCMC.py:55-60 through cuDNN).  Measure that drift here (the reference algorithm in eager PyTorch on this
+        # GPU, TF32 convolutions on) and hold the tensor-core mode to 2x it.
+        gen32 = [(W.to(dev), b.to(dev), s_, p_) for W, b, s_, p_ in synth.gen_list_from_state(gsd, layers, torch.float32)]
+        ebm32 = [(W.to(dev), b.to(dev)) for W, b in synth.ebm_list_from_state(esd, torch.float32)]
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            z_ref_tf32 = O.langevin_posterior(z0.to(dev), x.to(dev), gen32, ebm32, K, sigma, noise_on, step, noise.to(dev))
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+        tf32_drift = float(np.median(chain_errs(z_ref_tf32, g["z_f64"])))
+        print(f"{name}[tf32]: the reference's own TF32 run on this GPU drifts {tf32_drift:.3e} (median chain) from fp64")
+    assert_z_close(out, g, TOL[prec], name + f"[{prec}]", extra_drift=tf32_drift)
     assert out.data_ptr() == z.data_ptr()
     assert all(p.requires_grad for p in list(G.parameters()) + list(E.parameters()))
     # G(z_K) crop and the verbose trace agree with the reference
