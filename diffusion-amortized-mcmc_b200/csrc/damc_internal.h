@@ -153,6 +153,7 @@ struct GenPack : damc_handle {
   std::vector<damc_convt_layer> src;  // caller's tensors (for damc_repack)
   std::vector<void*> allocs;
   int dz_splits = 1;
+  bool last_fused = false;    // posterior steps run the last layer (forward, likelihood gradient, dgrad) as ONE launch (gen_last.cu)
   bool last_scatter = false;  // last layer runs as scatter-form GEMM + per-image finish kernel (image fits in smem)
   bool use_bits = false;    // tcgen05 engine: LeakyReLU masks travel as 1-bit-per-element words
   bool use_tc = false;      // bf16 mode: tcgen05 engine (default) or the SIMT engine on bf16 storage (DAMC_TC=0)
@@ -213,6 +214,7 @@ int launch_gemm_tc(const GemmPlan& p, int precision, cudaStream_t stream);
 struct TcLaunch;
 int tc_prepare(const GemmPlan& p, int precision, TcLaunch** out);
 int tc_encode_2d(void* tensor_map /* CUtensorMap* */, int fp16, const void* base, int cols, int rows, int box_rows);
+int tc_encode_act(void* tensor_map /* CUtensorMap* */, int precision, const void* base, int Cs, int Wm, int Hm, int B, int Ht);
 int tc_den_tile_width(int B, int Np);   // N tile width convgemm will use for a denoiser layer with Np = 4*dout columns
 GemmPlan* tc_plan(TcLaunch* l);
 int tc_launch(TcLaunch* l, cudaStream_t stream);
@@ -229,6 +231,11 @@ size_t last_finish_smem(const GenLayer& y);
 int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, const float* x, float* xhat,
                        float inv_sigma2, float gscale, float* loss, void* gcol, cudaStream_t stream);
 int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int precision, cudaStream_t stream);
+
+// fused last layer (scatter GEMM + col2im + tanh-likelihood gradient + K = 64 dgrad in one launch) -- gen_last.cu
+bool last_fused_supported(const GenPack* g);
+int launch_last_fused(const GenPack* g, const GenWorkspace& ws, int B, const float* x, float sigma, float* xhat, float* loss,
+                      cudaStream_t stream);
 
 // generator driver -- gen_driver.cu
 int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,

@@ -74,6 +74,7 @@ int build_generator(GenPack* g, int nlayers, const damc_convt_layer* L, float sl
   g->use_bits = g->use_tc && (precision == DAMC_PREC_TF32 || !getenv("DAMC_TC_NOBITS"));
   if (g->use_tc && !tc_available()) DAMC_FAIL(DAMC_ERR_CUDA, "bf16 mode needs cuTensorMapEncodeTiled from the driver (no fallback)");
   DAMC_TRY(g->refill(stream, nullptr));
+  g->last_fused = last_fused_supported(g);
   return handle_hash_init(g, stream);
 }
 
@@ -221,6 +222,13 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     e.slope = g->slope;
     e.bias = y.bias;
     e.sy = e.sx = y.type == L_UP ? 2 : 1;
+    if (last && g->last_fused && x != nullptr) {   // forward + likelihood gradient + this layer's dgrad in one launch
+      profile_mark(stream, true);
+      DAMC_TRY(launch_last_fused(g, ws, B, x, sigma, xhat, loss, stream));
+      profile_mark(stream, false);
+      count_launch();
+      continue;
+    }
     if (last && g->last_scatter) {
       p.N = y.n_sc; p.Np = y.np_sc;
       p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
@@ -277,7 +285,7 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
 
 int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream) {
   const int L = g->nlayers;
-  for (int l = L - 1; l >= 0; --l) {
+  for (int l = g->last_fused ? L - 2 : L - 1; l >= 0; --l) {   // the fused last-layer kernel has already produced grad[L-2]
     const GenLayer& y = g->layers[l];
     GemmPlan p{};
     p.B = B; p.Hm = y.Hin; p.Wm = y.Win;

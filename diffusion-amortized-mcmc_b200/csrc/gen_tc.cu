@@ -776,6 +776,25 @@ int tc_encode_2d(void* tensor_map, int fp16, const void* base, int cols, int row
   return DAMC_OK;
 }
 
+// NHWC activation tensor [B][Hm][Wm][Cs] (16-bit elements) as the 5-D map of the A operand: box {64 ch, Wm, Ht, 1, 1}, one
+// 128-byte swizzle row per pixel (used by the fused last-layer kernel, gen_last.cu)
+int tc_encode_act(void* tensor_map, int precision, const void* base, int Cs, int Wm, int Hm, int B, int Ht) {
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(tensor_map);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (!is_tc_precision(precision)) DAMC_FAIL(DAMC_ERR_INVALID, "tc_encode_act: 16-bit operand precisions only");
+  const cuuint64_t dims[5] = {(cuuint64_t)Cs, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)B, 1};
+  const cuuint64_t row = (cuuint64_t)Cs * 2;
+  const cuuint64_t strides[4] = {row, row * Wm, row * Wm * Hm, row * Wm * Hm * B};
+  const cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)Wm, (cuuint32_t)Ht, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(tm, precision == DAMC_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DAMC_FAIL(DAMC_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (Cs=%d W=%d H=%d B=%d)", (int)r, Cs, Wm, Hm, B);
+  return DAMC_OK;
+}
+
 // few chains: narrower N tiles spread one layer over more SMs and shorten each CTA's serial load -> MMA -> epilogue chain
 int tc_den_tile_width(int B, int Np) {
   int bn = Np < 256 ? Np : 256;

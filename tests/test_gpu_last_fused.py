@@ -1,0 +1,103 @@
+"""The fused last-layer kernel (csrc/gen_last.cu: scatter GEMM + col2im + tanh-likelihood gradient + K = 64 dgrad in one
+launch) against the three-launch form it replaces (scatter GEMM -> last_finish_kernel -> dgrad GEMM) and against the fp64
+oracle, for every last-layer family of the reference (diffusion_net.py:40-45 k3-s1-p1 nc=3, :195-197 nc=1, :76-78 /
+:161-163 k4-s2-p1), whole-image blocks and row blocks with halo recompute (CelebA-HQ 256x256)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import damc_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as ge
+    ge.build()
+    return torch.device("cuda:0")
+
+
+def _run(dataset, nz, ngf, nc, B, K, sigma, prec, fused, dev, want_xhat=False, noise_on=True):
+    from damc_b200 import MCMC, diffusion_net as dn
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=5, gain=0.0)
+    old = os.environ.get("DAMC_LAST_FUSED")
+    os.environ["DAMC_LAST_FUSED"] = "1" if fused else "0"     # read when the generator handle is packed
+    try:
+        G, E = dn._netG(dataset, nz, ngf, nc), dn._netE(nz)
+        G.load_state_dict(gsd)
+        E.load_state_dict(esd)
+        G, E = G.to(dev), E.to(dev)
+        z = z0.to(dev).clone().requires_grad_(True)
+        xh = torch.empty_like(x, device=dev) if want_xhat else None
+        n0 = MCMC.lib().damc_launch_count()
+        out = MCMC.sample_langevin_post_z_with_prior(z, x.to(dev), G, E, K, sigma, noise_on, 0.1, noise=noise.to(dev),
+                                                     precision=prec, x_hat_out=xh)
+        torch.cuda.synchronize()
+        launches = MCMC.lib().damc_launch_count() - n0
+    finally:
+        if old is None:
+            os.environ.pop("DAMC_LAST_FUSED", None)
+        else:
+            os.environ["DAMC_LAST_FUSED"] = old
+    return out.cpu().double(), (xh.cpu().double() if want_xhat else None), launches, (gsd, esd, z0, x, noise, layers)
+
+
+CASES = [  # dataset, nz, ngf, nc, B, sigma
+    ("cifar10", 128, 128, 3, 5, 0.1),      # k3-s1-p1, nc = 3, C = 256, whole-image blocks (8 tiles)
+    ("cifar10", 128, 64, 3, 3, 0.1),       # C = 128: one dgrad chunk per tile
+    ("svhn", 100, 64, 3, 7, 0.1),          # k4-s2-p1, C = 128, two tiles per image
+    ("mnist", 8, 128, 1, 5, 1.0),          # nc = 1, 28-wide rows: 112-row tiles
+    ("celeba64", 100, 64, 3, 2, 0.1),      # k4-s2-p1 at 32 -> 64, C = 64
+    ("celebaHQ", 128, 64, 3, 2, 1.0),      # 128-wide rows: one row per tile, row blocks with one halo tile on each side
+]
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 2e-3), ("fp16", 3e-4)])
+@pytest.mark.parametrize("dataset,nz,ngf,nc,B,sigma", CASES)
+def test_fused_last_layer_matches_three_launch_form(dataset, nz, ngf, nc, B, sigma, prec, tol, dev):
+    K = 2
+    zf, xf, lf, _ = _run(dataset, nz, ngf, nc, B, K, sigma, prec, True, dev, want_xhat=True)
+    zu, xu, lu, prob = _run(dataset, nz, ngf, nc, B, K, sigma, prec, False, dev, want_xhat=True)
+    assert lf == lu - 2 * K, (lf, lu)   # three launches became one, every step -- i.e. the fused kernel really ran
+    ez = float((zf - zu).abs().max() / zu.abs().max())
+    ex = float((xf - xu).abs().max())
+    print(f"{dataset} ngf={ngf} [{prec}]: fused vs three-launch  z {ez:.3e}  x_hat {ex:.3e}")
+    # same products, different fp32 summation order of the <= 9 col2im terms; a last-bit difference in x_hat can move the
+    # 16-bit rounding of a gradient entry, hence a tolerance at the operand rounding level rather than bit equality
+    assert ez < tol and ex < 5e-4, (ez, ex)   # x_hat is G at the (slightly different) z of step K-1
+    gsd, esd, z0, x, noise, layers = prob
+    gen64, ebm64 = synth.gen_list_from_state(gsd, layers, torch.float64), synth.ebm_list_from_state(esd, torch.float64)
+    ref = O.langevin_posterior(z0.double(), x.double(), gen64, ebm64, K, sigma, True, 0.1, noise.double())
+    er = float((zf - ref).abs().max() / ref.abs().max())
+    eu = float((zu - ref).abs().max() / ref.abs().max())
+    print(f"{dataset} ngf={ngf} [{prec}]: vs fp64 oracle  fused {er:.3e}  three-launch {eu:.3e}")
+    assert er < (2e-2 if prec == "bf16" else 4e-3)
+    assert er < 1.5 * eu + 1e-5
+
+
+def test_fused_last_layer_is_deterministic_and_batch_invariant(dev):
+    """A chain's result must not depend on how many other chains share the launch (blocks are per image) nor on the run."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    dataset, nz, ngf, nc, B, K, sigma = "svhn", 100, 64, 3, 300, 3, 0.1
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=5, gain=0.0)
+    G, E = dn._netG(dataset, nz, ngf, nc), dn._netE(nz)
+    G.load_state_dict(gsd)
+    E.load_state_dict(esd)
+    G, E = G.to(dev), E.to(dev)
+
+    def run(n):
+        z = z0[:n].to(dev).clone().requires_grad_(True)
+        return MCMC.sample_langevin_post_z_with_prior(z, x[:n].to(dev), G, E, K, sigma, True, 0.1,
+                                                      noise=noise[:, :n].contiguous().to(dev), precision="bf16").cpu()
+
+    full, again, few = run(B), run(B), run(9)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, again)
+    assert torch.equal(full[:9], few)
