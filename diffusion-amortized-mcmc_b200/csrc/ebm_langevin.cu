@@ -13,6 +13,8 @@
 // inside the loop except optional injected noise; z is read once and written once.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "damc_common.cuh"
 #include "damc_internal.h"
 
@@ -501,15 +503,16 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) gG[c] = 0.f;
     if (a.gpart != nullptr) {
-      for (int s0 = 0; s0 < a.nsplit; s0 += 8) {
-        float v[8][CH];
+      constexpr int SU = 32 / CH;   // splits per round trip: 32 independent loads in flight whatever the chain tile
+      for (int s0 = 0; s0 < a.nsplit; s0 += SU) {
+        float v[SU][CH];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < SU; ++u)
 #pragma unroll
           for (int c = 0; c < CH; ++c)
             v[u][c] = (s0 + u < a.nsplit && c < nvalid) ? a.gpart[((size_t)(s0 + u) * a.B + (size_t)(c0 + c)) * a.gstride + tid] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < SU; ++u)
 #pragma unroll
           for (int c = 0; c < CH; ++c) gG[c] += v[u][c];
       }
@@ -544,10 +547,10 @@ __global__ void __launch_bounds__(256) ebm_step_kernel(const EbmStepArgs a) {
   }
 }
 
-int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
-                    uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
-                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream, const unsigned long long* seed_ptr) {
-  constexpr int CH = 4;  // small chain tiles: two or more CTAs per SM overlap each other's L2 latency
+template <int CH>
+static int launch_ebm_step_ch(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
+                              uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
+                              float gpart_scale, int nz_if_no_ebm, cudaStream_t stream, const unsigned long long* seed_ptr) {
   EbmStepArgs a{};
   a.use_ebm = m != nullptr;
   if (m) {
@@ -563,10 +566,30 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
   a.gpart_scale = gpart_scale;
   a.inv_count = 1.0f / ((float)B * (float)a.nz);
   const size_t smem = sizeof(float) * CH * ((size_t)a.nz + 3 * (size_t)a.ndf);
+  if (smem > 48 * 1024) DAMC_CUDA(cudaFuncSetAttribute(ebm_step_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ebm_step_kernel<CH><<<ceil_div(B, CH), 256, smem, stream>>>(a);
   DAMC_CUDA(cudaGetLastError());
   count_launch();
   return DAMC_OK;
+}
+
+// Chain tile per CTA.  Every CTA streams the whole MLP (0.5 MB) from L2, so the launch moves B / CH x 0.5 MB: small tiles
+// (4 chains: two or more CTAs per SM overlap each other's L2 latency) while the grid is a few waves, larger ones once the
+// L2 -> SM stream is the bound (16 384 SVHN chains: 2.1 GB and 359 us with 4-chain tiles).  A chain's arithmetic (ascending-k
+// FMA chains, ascending split order) does not depend on the tile, so results are bit-identical across tile sizes.
+int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_noise, const float* noise, uint64_t seed,
+                    uint64_t chain0, uint64_t step_index, float* trace4, const float* gpart, int nsplit, int gstride,
+                    float gpart_scale, int nz_if_no_ebm, cudaStream_t stream, const unsigned long long* seed_ptr) {
+  static const int force = []{ const char* e = getenv("DAMC_EBM_CH"); return e ? atoi(e) : 0; }();
+  const int ch = force ? force : (B >= 16384 ? 16 : B >= 4096 ? 8 : 4);
+  if (ch >= 16)
+    return launch_ebm_step_ch<16>(m, z, B, step, with_noise, noise, seed, chain0, step_index, trace4, gpart, nsplit, gstride,
+                                  gpart_scale, nz_if_no_ebm, stream, seed_ptr);
+  if (ch >= 8)
+    return launch_ebm_step_ch<8>(m, z, B, step, with_noise, noise, seed, chain0, step_index, trace4, gpart, nsplit, gstride,
+                                 gpart_scale, nz_if_no_ebm, stream, seed_ptr);
+  return launch_ebm_step_ch<4>(m, z, B, step, with_noise, noise, seed, chain0, step_index, trace4, gpart, nsplit, gstride,
+                               gpart_scale, nz_if_no_ebm, stream, seed_ptr);
 }
 
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <atomic>
 
 #include "damc_common.cuh"
@@ -33,6 +34,7 @@ namespace damc {
 constexpr int LF_THREADS = 512;           // warp 0 TMA, 1 scatter-MMA, 2 dgrad-MMA, 3 idle, 4-7 S group, 8-15 E group
 constexpr int LF_TILE_BYTES = 128 * 128;  // 128 rows x one 128-byte swizzle row (64 16-bit elements)
 constexpr int LF_MAX_STAGES = 6;
+constexpr int LF_MAX_CHUNKS = 4;         // dgrad N chunks per tile (C <= 512)
 
 struct LastParams {
   int B, C, Hi, Wi, Ho, Wo, pad;
@@ -45,8 +47,12 @@ struct LastParams {
   int stages;
   uint32_t idesc_sc, idesc_dg;
   int op_fp16;
-  uint32_t off_a2, off_wsc, off_wdg, off_out, off_g, off_bar;   // bytes from the 1024-aligned smem base
+  uint32_t off_a2, off_wsc, off_wdg, off_out, off_g, off_x, off_bar;   // bytes from the 1024-aligned smem base
   int out_floats, g_bytes;
+  int wo_shift;                // log2(Wo) or -1
+  int xr;                      // output rows of x held in smem at a time (>= n_need: the whole block in one chunk)
+  int row_in_warp;             // 32 % Wi == 0: an image row never straddles two warps of the S group
+  int debug;                   // DAMC_LAST_DEBUG=1: CTA 0 prints where its warp groups spent their clocks
   const float* x;              // [B][nc][Ho][Wo]
   float* xhat;                 // same shape or null
   float* loss;                 // scalar accumulator or null
@@ -57,9 +63,17 @@ struct LastParams {
   int planar_out;
 };
 
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+#define LF_T(acc, stmt) do { if (P.debug) { const uint32_t _t = (uint32_t)clock(); stmt; acc += (uint32_t)clock() - _t; } else { stmt; } } while (0)
 
 struct LastBlock {
   int b, t0, t1, pt0, pt1, r0, r1, need_lo, n_need;
@@ -100,8 +114,9 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto bar_a2empty = [&](int a) { return bars + 8u * (2 * LF_MAX_STAGES + 9 + a); };
   auto bar_t3full = [&](int a) { return bars + 8u * (2 * LF_MAX_STAGES + 11 + a); };
   auto bar_t3empty = [&](int a) { return bars + 8u * (2 * LF_MAX_STAGES + 13 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * LF_MAX_STAGES + 15);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + P.off_bar + 8u * (2 * LF_MAX_STAGES + 15));
+  const uint32_t bar_xfull = bars + 8u * (2 * LF_MAX_STAGES + 15);
+  const uint32_t tmem_slot = bars + 8u * (2 * LF_MAX_STAGES + 16);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + P.off_bar + 8u * (2 * LF_MAX_STAGES + 16));
   float* const out_s = reinterpret_cast<float*>(gen_base + P.off_out);
   uint8_t* const g_s = gen_base + P.off_g;
 
@@ -120,6 +135,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_init(bar_gfull, 4);
     mbar_init(bar_gempty, 8);
+    mbar_init(bar_xfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -162,15 +178,16 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(bar_w, 0u);
       tc_fence_after();
       int stage = 0, it = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, dbg0 = 0, dbg1 = 0;
+      const uint32_t tstart = (uint32_t)clock();
       for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x) {
         const LastBlock L = last_block<K, S>(P, blk);
         for (int t = L.pt0; t < L.pt1; ++t, ++it) {
           const int as = it & 1;
-          mbar_wait(bar_yempty(as), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          LF_T(dbg0, mbar_wait(bar_yempty(as), ((uint32_t)(it >> 1) & 1u) ^ 1u));
           tc_fence_after();
           for (int kb = 0; kb < P.kb_sc; ++kb) {
-            mbar_wait(bar_full(stage), phase);
+            LF_T(dbg1, mbar_wait(bar_full(stage), phase));
             tc_fence_after();
             const uint64_t adesc = make_sdesc(base + (uint32_t)stage * LF_TILE_BYTES);
             const uint64_t bdesc = make_sdesc(base + P.off_wsc + (uint32_t)(kb * P.Np_sc * 128));
@@ -184,6 +201,8 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           umma_commit(bar_yfull(as));
         }
       }
+      if (P.debug && blockIdx.x == 0)
+        printf("last_fused CTA0 scatter-MMA: total %u clk, wait yempty %u, wait A tiles %u, tiles %d\n", (uint32_t)clock() - tstart, dbg0, dbg1, it);
     }
   } else if (warp == 2) {
     // ===================== dgrad-GEMM issuer =====================
@@ -191,16 +210,17 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(bar_w, 0u);
       tc_fence_after();
       int jt = 0, jc = 0;
+      uint32_t dbg0 = 0, dbg1 = 0;
       for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x) {
         const LastBlock L = last_block<K, S>(P, blk);
         for (int t = L.t0; t < L.t1; ++t, ++jt) {
           const int buf = jt & 1;
-          mbar_wait(bar_a2full(buf), (uint32_t)(jt >> 1) & 1u);
+          LF_T(dbg0, mbar_wait(bar_a2full(buf), (uint32_t)(jt >> 1) & 1u));
           tc_fence_after();
           const uint64_t adesc = make_sdesc(base + P.off_a2 + (uint32_t)buf * LF_TILE_BYTES);
           for (int ch = 0; ch < P.nchunks; ++ch, ++jc) {
             const int st = jc & 1;
-            mbar_wait(bar_t3empty(st), ((uint32_t)(jc >> 1) & 1u) ^ 1u);
+            LF_T(dbg1, mbar_wait(bar_t3empty(st), ((uint32_t)(jc >> 1) & 1u) ^ 1u));
             tc_fence_after();
             const uint64_t bdesc = make_sdesc(base + P.off_wdg + (uint32_t)(ch * P.chunkN * 128));
 #pragma unroll
@@ -211,6 +231,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           umma_commit(bar_a2empty(buf));
         }
       }
+      if (P.debug && blockIdx.x == 0) printf("last_fused CTA0 dgrad-MMA: wait operand tile %u, wait accumulator %u\n", dbg0, dbg1);
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== S group: col2im accumulation (P1) and the likelihood gradient (P2) =====================
@@ -221,20 +242,26 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const float gmul = P.inv_sigma2 * P.gscale;
     int it = 0, nb = 0;
     float loss_acc = 0.f;
+    uint32_t dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
+    uint32_t nx = 0;   // x chunks consumed so far (parity of bar_xfull)
+    const float* x_s = reinterpret_cast<const float*>(gen_base + P.off_x);
+    // rows [need_lo + lr0, +xr) of the block, clipped to the image: one contiguous run per channel
+    auto issue_x = [&](const LastBlock& L, int lr0) {
+      const int oy0 = max(0, L.need_lo + lr0), oy1 = min(P.Ho, L.need_lo + min(L.n_need, lr0 + P.xr));
+      const uint32_t bytes = (uint32_t)((oy1 - oy0) * P.Wo * 4);
+      mbar_expect_tx(bar_xfull, bytes * NC);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        bulk_load_1d(base + P.off_x + (uint32_t)(c * P.xr * P.Wo * 4), P.x + (((size_t)L.b * NC + c) * P.Ho + oy0) * P.Wo, bytes, bar_xfull);
+    };
     for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x, ++nb) {
       const LastBlock L = last_block<K, S>(P, blk);
-      {  // pull this block's x rows towards L2 while the scatter GEMM runs
-        const int oy0 = max(0, L.need_lo), oy1 = min(P.Ho, L.need_lo + L.n_need);
-        const int lines = ((oy1 - oy0) * P.Wo * 4 + 127) / 128;
-        for (int c = 0; c < NC; ++c) {
-          const char* p0 = reinterpret_cast<const char*>(P.x + (((size_t)L.b * NC + c) * P.Ho + oy0) * P.Wo);
-          for (int i = sid; i < lines; i += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (size_t)i * 128));
-        }
-      }
+      if (sid == 0) issue_x(L, 0);   // this block's x rows (first chunk) travel while the scatter GEMM runs
       for (int t = L.pt0; t < L.pt1; ++t, ++it) {
         const int as = it & 1;
-        mbar_wait_relaxed(bar_yfull(as), (uint32_t)(it >> 1) & 1u);
+        LF_T(dbg0, mbar_wait(bar_yfull(as), (uint32_t)(it >> 1) & 1u));
         tc_fence_after();
+        const uint32_t tp1 = P.debug ? (uint32_t)clock() : 0u;
         uint32_t v[NLD];
         if constexpr (NLD == 16) {
           tmem_ld16(t_lane + (uint32_t)as * 64u, v);
@@ -253,57 +280,126 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool valid = r < P.tile_rows;
         const int ry = r / P.Wi;
         const int iy = t * P.Ht + ry, ix = r - ry * P.Wi;
-        constexpr int G = S == 2 ? 2 : 1;   // slots per dimension whose targets cannot collide within one pass
+        // col2im: every thread adds its pixel's K*K*NC products into the pre-activation image.  Two threads may not add to
+        // the same pixel concurrently, and the order of the additions must be fixed (bit-reproducible results), so the
+        // slots are visited in passes whose targets are distinct across the group, separated by barriers.
+        auto tgt = [&](int kh, int kw, bool& ok) -> float* {
+          const int oy = iy * S - P.pad + kh, ox = ix * S - P.pad + kw, lrow = oy - L.need_lo;
+          ok = valid && oy >= 0 && oy < P.Ho && lrow >= 0 && lrow < L.n_need && ox >= 0 && ox < P.Wo;
+          return out_s + (lrow * P.Wo + ox) * NC;
+        };
+        if constexpr (S == 2) {
+          // stride 2: the 2 x 2 slots {kh0, kh0+1} x {kw0, kw0+1} of ALL threads land on distinct pixels (distinct output
+          // parities) -- one pass of 4 slots, loads batched ahead of the stores.  Passes that differ only in kw0 collide
+          // only between horizontal neighbours: lanes of one warp when an image row does not straddle warps.
 #pragma unroll
-        for (int kh0 = 0; kh0 < K; kh0 += G)
+          for (int kh0 = 0; kh0 < K; kh0 += 2)
 #pragma unroll
-          for (int kw0 = 0; kw0 < K; kw0 += G) {
+            for (int kw0 = 0; kw0 < K; kw0 += 2) {
+              float* tp[4];
+              bool ok[4];
+              float tv[4][NC];
 #pragma unroll
-            for (int a = 0; a < G; ++a)
+              for (int j = 0; j < 4; ++j) tp[j] = tgt(kh0 + (j >> 1), kw0 + (j & 1), ok[j]);
 #pragma unroll
-              for (int b2 = 0; b2 < G; ++b2) {
-                const int kh = kh0 + a, kw = kw0 + b2;
-                const int oy = iy * S - P.pad + kh, ox = ix * S - P.pad + kw, lrow = oy - L.need_lo;
-                if (valid && oy >= 0 && oy < P.Ho && lrow >= 0 && lrow < L.n_need && ox >= 0 && ox < P.Wo) {
-                  float* op = out_s + (lrow * P.Wo + ox) * NC;
+              for (int j = 0; j < 4; ++j)
 #pragma unroll
-                  for (int c = 0; c < NC; ++c) op[c] += __uint_as_float(v[(kh * K + kw) * NC + c]);
+                for (int c = 0; c < NC; ++c) tv[j][c] = ok[j] ? tp[j][c] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (ok[j]) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c)
+                    tp[j][c] = tv[j][c] + __uint_as_float(v[((kh0 + (j >> 1)) * K + kw0 + (j & 1)) * NC + c]);
                 }
+              if (P.row_in_warp && kw0 + 2 < K) __syncwarp(); else named_bar_sync(1, 128);
+            }
+        } else {
+          if (P.row_in_warp) {
+            // stride 1, rows inside a warp: the three kw terms of an output pixel come from lanes ix+1, ix, ix-1 -- summed
+            // through shuffles, then ONE add per kh (distinct pixels across the group)
+            const bool has_r = ix + 1 < P.Wi, has_l = ix > 0;
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+              float tsum[NC];
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {
+                const float fr = __shfl_down_sync(0xffffffffu, __uint_as_float(v[(kh * K + 0) * NC + c]), 1);
+                const float fl = __shfl_up_sync(0xffffffffu, __uint_as_float(v[(kh * K + 2) * NC + c]), 1);
+                tsum[c] = ((has_r ? fr : 0.f) + __uint_as_float(v[(kh * K + 1) * NC + c])) + (has_l ? fl : 0.f);
               }
-            named_bar_sync(1, 128);
-          }
-      }
-      // ---- P2: x_hat, loss, likelihood gradient -------------------------------------------------------------------
-      mbar_wait_relaxed(bar_gempty, ((uint32_t)nb & 1u) ^ 1u);   // the E group has gathered the previous block's gradient image
-      const int npx = L.n_need * P.Wo;
-      const int own0 = L.r0 * S, own1 = L.r1 * S;
-      for (int p = sid; p < npx; p += 128) {
-        const int lrow = p / P.Wo, ox = p - lrow * P.Wo, oy = L.need_lo + lrow;
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (oy >= 0 && oy < P.Ho) {
-          float* op = out_s + p * NC;
-          const bool own = oy >= own0 && oy < own1;
-          float h[NC], xv[NC];
+              bool ok;
+              float* tp = tgt(kh, 1, ok);
+              if (ok) {
 #pragma unroll
-          for (int c = 0; c < NC; ++c) xv[c] = __ldg(P.x + (((size_t)L.b * NC + c) * P.Ho + oy) * P.Wo + ox);
+                for (int c = 0; c < NC; ++c) tp[c] += tsum[c];
+              }
+              named_bar_sync(1, 128);
+            }
+          } else {
 #pragma unroll
-          for (int c = 0; c < NC; ++c) { h[c] = op[c]; op[c] = bias_r[c]; }
+            for (int kh = 0; kh < K; ++kh)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const float xh = tanhf(h[c]);
-            if (P.xhat != nullptr && own) P.xhat[(((size_t)L.b * NC + c) * P.Ho + oy) * P.Wo + ox] = xh;
-            const float rr = xh - xv[c];
-            g[c] = rr * gmul * (1.f - xh * xh);
-            if (own) loss_acc += 0.5f * P.inv_sigma2 * rr * rr;
+              for (int kw = 0; kw < K; ++kw) {
+                bool ok;
+                float* tp = tgt(kh, kw, ok);
+                if (ok) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) tp[c] += __uint_as_float(v[(kh * K + kw) * NC + c]);
+                }
+                named_bar_sync(1, 128);
+              }
           }
         }
-        const uint32_t w0 = pack2(P.op_fp16, g[0], g[1]), w1 = pack2(P.op_fp16, g[2], g[3]);
-        *reinterpret_cast<uint2*>(g_s + (size_t)lrow * gpitch + (size_t)(ox + 1) * 8) = make_uint2(w0, w1);
+        if (P.debug) dbg1 += (uint32_t)clock() - tp1;
       }
+      // ---- P2: x_hat, loss, likelihood gradient -------------------------------------------------------------------
+      // x arrives in smem by bulk copies issued at the START of the block (a dependent global load per pixel would expose a
+      // loaded-DRAM round trip per iteration, ~3 k clocks each); blocks whose rows do not fit take it in several chunks.
+      const int own0 = L.r0 * S, own1 = L.r1 * S;
+      LF_T(dbg2, mbar_wait(bar_gempty, ((uint32_t)nb & 1u) ^ 1u));   // the E group has gathered the previous block's gradient image
+      const uint32_t tp2 = P.debug ? (uint32_t)clock() : 0u;
+      for (int lr0 = 0; lr0 < L.n_need; lr0 += P.xr) {
+        const int lr1 = min(L.n_need, lr0 + P.xr);
+        if (lr0 > 0) {   // later chunk: every thread is done with the buffer, then one thread refills it
+          named_bar_sync(1, 128);
+          if (sid == 0) issue_x(L, lr0);
+        }
+        mbar_wait(bar_xfull, nx & 1u);
+        ++nx;
+        const int cy0 = max(0, L.need_lo + lr0);   // first image row held by the buffer
+        // (a 4-pixel batched form of this loop measured 3-8 % slower on the 3-channel shapes: more live registers, same chain)
+        for (int p = lr0 * P.Wo + sid; p < lr1 * P.Wo; p += 128) {
+          const int lrow = P.wo_shift >= 0 ? (p >> P.wo_shift) : p / P.Wo;
+          const int ox = p - lrow * P.Wo, oy = L.need_lo + lrow;
+          float g[4] = {0.f, 0.f, 0.f, 0.f};
+          if (oy >= 0 && oy < P.Ho) {
+            float* op = out_s + p * NC;
+            const bool own = oy >= own0 && oy < own1;
+            float h[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { h[c] = op[c]; op[c] = bias_r[c]; }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              // tanh(h) = 1 - 2 / (e^{2h} + 1): absolute error ~1e-7 (x_hat enters only through x_hat - x and 1 - x_hat^2)
+              const float xh = 1.f - __fdividef(2.f, __expf(2.f * h[c]) + 1.f);
+              if (P.xhat != nullptr && own) P.xhat[(((size_t)L.b * NC + c) * P.Ho + oy) * P.Wo + ox] = xh;
+              const float rr = xh - x_s[(c * P.xr + (oy - cy0)) * P.Wo + ox];
+              g[c] = rr * gmul * (1.f - xh * xh);
+              if (own) loss_acc += 0.5f * P.inv_sigma2 * rr * rr;
+            }
+          }
+          const uint32_t w0 = pack2(P.op_fp16, g[0], g[1]), w1 = pack2(P.op_fp16, g[2], g[3]);
+          *reinterpret_cast<uint2*>(g_s + (size_t)lrow * gpitch + (size_t)(ox + 1) * 8) = make_uint2(w0, w1);
+        }
+      }
+      if (P.debug) dbg3 += (uint32_t)clock() - tp2;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfull);   // release: this warp's gradient pixels are visible to the E group
       named_bar_sync(1, 128);                  // every pre-activation is re-initialised before the next block accumulates
     }
+    if (P.debug && blockIdx.x == 0 && sid == 0)
+      printf("last_fused CTA0 S group: wait scatter acc %u, col2im %u, wait gempty %u, P2 %u, blocks %d\n", dbg0, dbg1, dbg2, dbg3, nb);
     if (P.loss != nullptr) {
       loss_acc = warp_sum(loss_acc);
       if (lane == 0 && loss_acc != 0.f) atomicAdd(P.loss, loss_acc);
@@ -312,41 +408,63 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== E group: operand gather (P3a) and the masked dgrad epilogue (P3b) =====================
     const int q = warp & 3, half = (warp - 8) >> 2, eid = threadIdx.x - 256;
     int jb = 0, jc = 0, nb = 0;
+    uint32_t dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0, dbg4 = 0;
     const int cw = P.chunkN >> 1;   // columns of a chunk handled by this warp
     const uint32_t t_lane = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * cw);
+    uint32_t mnext[LF_MAX_CHUNKS][2];
+    // sign-bit words of this lane's row of tile t: cw columns of every chunk (1 bit per element of a, NHWC order)
+    auto load_masks = [&](int b, int t, uint32_t (&mw)[LF_MAX_CHUNKS][2]) {
+      const int r = q * 32 + lane;
+      const int ry = r / P.Wi;
+      const long long m = r < P.tile_rows ? ((long long)b * P.Hi + t * P.Ht + ry) * P.Wi + (r - ry * P.Wi) : 0ll;
+      const uint32_t* mrow = P.maskbits + ((m * P.C) >> 5);
+#pragma unroll
+      for (int ch = 0; ch < LF_MAX_CHUNKS; ++ch) {
+        mw[ch][0] = mw[ch][1] = 0u;
+        if (ch < P.nchunks) {
+          const int n0 = ch * P.chunkN + half * cw;
+          mw[ch][0] = __ldg(mrow + (n0 >> 5));
+          if (cw > 32) mw[ch][1] = __ldg(mrow + (n0 >> 5) + 1);
+        }
+      }
+    };
     for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x, ++nb) {
       const LastBlock L = last_block<K, S>(P, blk);
-      mbar_wait_relaxed(bar_gfull, (uint32_t)nb & 1u);
+      load_masks(L.b, L.t0, mnext);   // the block's first tile: in flight while the S group finishes the gradient image
+      LF_T(dbg0, mbar_wait(bar_gfull, (uint32_t)nb & 1u));
       auto build = [&](int t) {
         const int buf = jb & 1;
-        mbar_wait_relaxed(bar_a2empty(buf), ((uint32_t)(jb >> 1) & 1u) ^ 1u);
-        const int r = eid >> 1, hf = eid & 1;
+        LF_T(dbg1, mbar_wait(bar_a2empty(buf), ((uint32_t)(jb >> 1) & 1u) ^ 1u));
+        const uint32_t tb = P.debug ? (uint32_t)clock() : 0u;
+        const int r = eid & 127, hf = eid >> 7;   // warp-uniform half: no divergence between the two compile-time slot lists
         if (r < P.tile_rows) {
           const int ry = r / P.Wi;
           const int iy = t * P.Ht + ry, ix = r - ry * P.Wi;
           const uint32_t row = base + P.off_a2 + (uint32_t)buf * LF_TILE_BYTES + (uint32_t)r * 128u;
+          const uint8_t* gpix = g_s + (size_t)(iy * S - P.pad - L.need_lo) * gpitch + (size_t)(ix * S - P.pad + 1) * 8;   // slot (0,0)
+          auto gather_half = [&](auto HF) {   // slots [8 HF, 8 HF + 8): (kh, kw) are compile-time constants
+            constexpr int hfc = decltype(HF)::value;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = hf * 4 + jj;
-            uint2 s01[2];
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = hfc * 4 + jj;
+              uint2 s01[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int slot = 2 * j + u;
-              s01[u] = make_uint2(0u, 0u);
-              if (slot < K * K) {
-                const int kh = slot / K, kw = slot - kh * K;
-                const int lrow = iy * S - P.pad + kh - L.need_lo, oxp = ix * S - P.pad + kw + 1;
-                s01[u] = *reinterpret_cast<const uint2*>(g_s + (size_t)lrow * gpitch + (size_t)oxp * 8);
+              for (int u = 0; u < 2; ++u) {
+                const int slot = 2 * j + u;
+                s01[u] = make_uint2(0u, 0u);
+                if (slot < K * K) s01[u] = *reinterpret_cast<const uint2*>(gpix + (size_t)(slot / K) * gpitch + (size_t)(slot % K) * 8);
               }
+              const uint32_t dst = row + (uint32_t)((j ^ (r & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(s01[0].x), "r"(s01[0].y), "r"(s01[1].x), "r"(s01[1].y) : "memory");
             }
-            const uint32_t dst = row + (uint32_t)((j ^ (r & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(s01[0].x), "r"(s01[0].y), "r"(s01[1].x), "r"(s01[1].y) : "memory");
-          }
+          };
+          if (hf == 0) gather_half(std::integral_constant<int, 0>{}); else gather_half(std::integral_constant<int, 1>{});
         }
         fence_proxy_async();   // generic-proxy writes of the operand tile -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a2full(buf));
         ++jb;
+        if (P.debug) dbg2 += (uint32_t)clock() - tb;
       };
       auto done_gather = [&]() {   // this warp has read everything it needs from the block's gradient image
         __syncwarp();
@@ -372,43 +490,57 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           o = m * P.C;
         }
         const unsigned long long out_row = (unsigned long long)P.gout + 2ull * (unsigned long long)(valid ? o : 0ll);
-        const uint32_t* mrow = P.maskbits + ((m * P.C) >> 5);
-        for (int ch = 0; ch < P.nchunks; ++ch, ++jc) {
-          const int st = jc & 1;
-          const int n0 = ch * P.chunkN + half * cw;
-          uint32_t mw[2] = {0u, 0u};
-          mw[0] = __ldg(mrow + (n0 >> 5));
-          if (cw > 32) mw[1] = __ldg(mrow + (n0 >> 5) + 1);
-          mbar_wait_relaxed(bar_t3full(st), (uint32_t)(jc >> 1) & 1u);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c32 = 0; c32 < cw; c32 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + (uint32_t)st * 128u + (uint32_t)c32, v);
-            tmem_ld_wait();
-            const uint32_t mword = mw[c32 >> 5];
+        // this tile's sign bits were requested one tile ago; request the next tile's now (a load issued where it is used
+        // would expose a loaded-memory round trip per chunk)
+        uint32_t mcur[LF_MAX_CHUNKS][2];
 #pragma unroll
-            for (int h16 = 0; h16 < 2; ++h16) {
-              uint32_t w[8];
+        for (int ch = 0; ch < LF_MAX_CHUNKS; ++ch) { mcur[ch][0] = mnext[ch][0]; mcur[ch][1] = mnext[ch][1]; }
+        if (t + 1 < L.t1) load_masks(L.b, t + 1, mnext);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int c0 = 16 * h16 + 2 * e;
-                const float s0 = (mword & (1u << c0)) ? 1.f : P.slope, s1 = (mword & (1u << (c0 + 1))) ? 1.f : P.slope;
-                w[e] = pack2(P.op_fp16, __uint_as_float(v[c0]) * s0, __uint_as_float(v[c0 + 1]) * s1);
-              }
-              if (valid) {
-                const unsigned long long a = out_row + 2ull * (unsigned long long)(n0 + c32 + 16 * h16);
-                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                             "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        for (int ch = 0; ch < LF_MAX_CHUNKS; ++ch) {
+          if (ch < P.nchunks) {
+            const int st = jc & 1;
+            const int n0 = ch * P.chunkN + half * cw;
+            LF_T(dbg3, mbar_wait(bar_t3full(st), (uint32_t)(jc >> 1) & 1u));
+            tc_fence_after();
+            const uint32_t te = P.debug ? (uint32_t)clock() : 0u;
+#pragma unroll
+            for (int i32 = 0; i32 < 2; ++i32) {
+              const int c32 = 32 * i32;
+              if (c32 < cw) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)st * 128u + (uint32_t)c32, v);
+                tmem_ld_wait();
+                const uint32_t mword = mcur[ch][i32];
+#pragma unroll
+                for (int h16 = 0; h16 < 2; ++h16) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int c0 = 16 * h16 + 2 * e;
+                    const float s0 = (mword & (1u << c0)) ? 1.f : P.slope, s1 = (mword & (1u << (c0 + 1))) ? 1.f : P.slope;
+                    w[e] = pack2(P.op_fp16, __uint_as_float(v[c0]) * s0, __uint_as_float(v[c0 + 1]) * s1);
+                  }
+                  if (valid) {
+                    const unsigned long long a = out_row + 2ull * (unsigned long long)(n0 + c32 + 16 * h16);
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                  }
+                }
               }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t3empty(st));
+            if (P.debug) dbg4 += (uint32_t)clock() - te;
+            ++jc;
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t3empty(st));
         }
       }
     }
+    if (P.debug && blockIdx.x == 0 && eid == 0)
+      printf("last_fused CTA0 E group: wait gfull %u, wait operand buffer %u, gather %u, wait dgrad acc %u, epilogue %u, chunks %d\n",
+             dbg0, dbg1, dbg2, dbg3, dbg4, jc);
   }
   tc_fence_before();
   __syncthreads();
@@ -447,26 +579,37 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   if (P.Np_sc > 64 || P.Np_sc != (y.k * y.k * y.cout + 15) / 16 * 16) return false;
   const int halo_rows = same ? 2 : 1;
   const size_t wbytes = (size_t)P.kb_sc * P.Np_sc * 128 + (size_t)y.cin * 128;
-  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 15) + 64 + 1024;
+  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 16) + 64 + 1024;
   const size_t cap = 227 * 1024;
   auto need_rows = [&](int Rt) { return (Rt * P.Ht - 1) * y.stride - y.pad + y.k - 1 - (0 * y.stride - y.pad) + 1; };
-  int best_rt = 0, best_stages = 0;
-  for (int Rt = P.tpi; Rt >= 1; --Rt) {
+  if (P.nchunks > LF_MAX_CHUNKS) return false;
+  int best_rt = 0, best_stages = 0, best_xr = 0;
+  for (int Rt = P.tpi; Rt >= 1 && !best_rt; --Rt) {
     if (Rt < P.tpi && Rt > 16) continue;
-    const size_t img = align_up((size_t)need_rows(Rt) * y.Wout * y.cout * 4, 16) + align_up((size_t)need_rows(Rt) * (y.Wout + 2) * 8, 16);
-    if (fixed + img + 4 * LF_TILE_BYTES > cap) continue;   // at least a 4-stage activation ring
-    best_rt = Rt;
-    best_stages = (int)std::min<size_t>(LF_MAX_STAGES, (cap - fixed - img) / LF_TILE_BYTES);
-    break;
+    const int nr = need_rows(Rt);
+    for (int xchunks = 1; xchunks <= 3 && !best_rt; ++xchunks) {   // x rows staged per bulk copy: the whole block, or 1/2, 1/3 of it
+      const int xr = ceil_div(nr, xchunks);
+      const size_t img = align_up((size_t)nr * y.Wout * y.cout * 4, 16) + align_up((size_t)nr * (y.Wout + 2) * 8, 16) +
+                         align_up((size_t)y.cout * xr * y.Wout * 4, 16);
+      if (fixed + img + 4 * LF_TILE_BYTES > cap) continue;   // at least a 4-stage activation ring
+      best_rt = Rt;
+      best_xr = xr;
+      best_stages = (int)std::min<size_t>(LF_MAX_STAGES, (cap - fixed - img) / LF_TILE_BYTES);
+    }
   }
   if (!best_rt) return false;
+  if ((y.Wout * 4) % 16) return false;   // bulk copies move whole 16-byte units
   P.Rt = best_rt;
   P.stages = best_stages;
+  P.xr = best_xr;
+  P.row_in_warp = (32 % y.Win == 0) ? 1 : 0;
   P.halo_t = P.Rt == P.tpi ? 0 : ceil_div(halo_rows, P.Ht);
   P.nblk_img = ceil_div(P.tpi, P.Rt);
   P.nblocks = B * P.nblk_img;
   const int nr = need_rows(P.Rt);
   P.out_floats = nr * y.Wout * y.cout;
+  P.wo_shift = -1;
+  for (int l2 = 0; l2 < 12; ++l2) if ((1 << l2) == y.Wout) P.wo_shift = l2;
   P.g_bytes = (int)align_up((size_t)nr * (y.Wout + 2) * 8, 16);
   uint32_t off = (uint32_t)P.stages * LF_TILE_BYTES;
   P.off_a2 = off; off += 2 * LF_TILE_BYTES;
@@ -475,8 +618,9 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   P.off_wdg = off; off += (uint32_t)(y.cin * 128);
   P.off_out = off; off += (uint32_t)align_up((size_t)P.out_floats * 4, 16);
   P.off_g = off; off += (uint32_t)P.g_bytes;
+  P.off_x = off; off += (uint32_t)align_up((size_t)y.cout * P.xr * y.Wout * 4, 16);
   P.off_bar = (uint32_t)align_up(off, 8);
-  const size_t total = P.off_bar + 8 * (2 * LF_MAX_STAGES + 15) + 16 + 1024;
+  const size_t total = P.off_bar + 8 * (2 * LF_MAX_STAGES + 16) + 16 + 1024;
   if (total > cap) return false;
   const uint32_t opfmt = g->precision == DAMC_PREC_FP16 ? 0u : 1u;
   P.op_fp16 = g->precision == DAMC_PREC_FP16 ? 1 : 0;
@@ -508,6 +652,7 @@ int launch_last_fused(const GenPack* g, const GenWorkspace& ws, int B, const flo
   P.maskbits = ws.mask[L - 2];
   P.gout = ws.grad[L - 2];
   P.planar_out = g->layers[L - 2].type == L_UP ? 1 : 0;
+  { const char* e = getenv("DAMC_LAST_DEBUG"); P.debug = (e && e[0] == '1') ? 1 : 0; }
   CUtensorMap tmA, tmWsc, tmWdg;
   DAMC_TRY(tc_encode_act(&tmA, g->precision, ws.act[L - 2], y.cin, y.Win, y.Hin, B, P.Ht));
   DAMC_TRY(tc_encode_2d(&tmWsc, P.op_fp16, y.w_scatter_tc, y.cin, P.Np_sc, P.Np_sc));

@@ -879,7 +879,14 @@ static int tc_prepare_into(const GemmPlan& p, int precision, TcLaunch* L) {
   const int ew = (P.stage_cols && P.kb_per_split <= 4 && P.BN >= 256 && !getenv("DAMC_TC_EW8")) ? 16 : 8;
   // CTA-pair MMA for the MMA-bound launches: full 256-wide N tiles, long K, an even grid of pairs
   static const bool allow_2sm = []{ const char* e = getenv("DAMC_TC_2SM"); return !(e && e[0] == '0'); }();
-  const int cg = (allow_2sm && ew == 8 && P.BN == 256 && p.Np % 256 == 0 && P.kb_per_split >= 16 && P.m_tiles >= 2) ? 2 : 1;
+  // (also for genuinely 128-wide layers -- SVHN 256->128, CelebA-HQ 256->128 forward: a 256 x 128 pair tile stages 24 KB per
+  //  k-block and CTA instead of 32 KB for two independent 128 x 128 tiles, and each MMA reads half of the weight rows)
+  // Measured (profiles/r02_launches_*): no gain -- SVHN 256->128 forward 1 440 us as pairs vs 1 313 us as single CTAs, CelebA-HQ
+  // 744 vs 666 us; both forms move > 21 TB/s of L2 -> SM operand traffic at full tensor rate, which the fabric does not
+  // deliver (17-18 TB/s measured), so 128-wide layers are L2 -> SM bound either way.  Off by default.
+  static const bool pair_n128 = []{ const char* e = getenv("DAMC_TC_PAIR128"); return e && e[0] == '1'; }();
+  const bool pair_shape = (P.BN == 256 && p.Np % 256 == 0) || (pair_n128 && P.BN == 128 && p.Np == 128 && !den_kind);
+  const int cg = (allow_2sm && ew == 8 && pair_shape && P.kb_per_split >= 16 && P.m_tiles >= 2) ? 2 : 1;
   P.fd_munits = make_fastdiv(ceil_div(P.m_tiles, cg));
   if (cg == 2) P.b_box_bytes /= 2;  // each CTA of the pair stages half of the 256 weight rows
   if (den_kind) P.b_box_bytes /= 2; // denoiser: a k-block loads only the column block (half of the tile's rows) it feeds
