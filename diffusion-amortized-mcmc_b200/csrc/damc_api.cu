@@ -274,6 +274,22 @@ int damc_generator_forward(const damc_handle* gen, const float* z, float* x_hat,
   return generator_forward(g, ws, z, B, nullptr, 1.0f, x_hat, nullptr, (cudaStream_t)stream);
 }
 
+int damc_posterior_score(const damc_handle* gen, const damc_handle* ebm, const float* z, const float* x, int B, float* score,
+                         float* sqerr, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gen || gen->kind != H_GEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_score: not a generator handle");
+  if (ebm && ebm->kind != H_MLP) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_score: not an EBM handle");
+  if (!z || !x || B <= 0 || (!score && !sqerr)) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_score: bad arguments");
+  const GenPack* g = static_cast<const GenPack*>(gen);
+  const MlpPack* m = static_cast<const MlpPack*>(ebm);
+  if (m && m->nz != g->nz) DAMC_FAIL(DAMC_ERR_INVALID, "EBM nz %d != generator nz %d", m->nz, g->nz);
+  GenWorkspace ws;
+  plan_workspace(g, B, workspace, &ws);
+  if (!workspace || workspace_bytes < ws.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  DAMC_TRY(generator_score_forward(g, ws, z, B, x, s));
+  return launch_ebm_score(m, z, B, g->nz, ws.sq_part, score_parts(g), score, sqerr, s);
+}
+
 int damc_prior_langevin(const damc_handle* ebm, float* z, int B, int K, float step_size, int with_noise,
                         const float* noise, uint64_t seed, uint64_t chain0, uint64_t step0, float* trace,
                         void* stream) {

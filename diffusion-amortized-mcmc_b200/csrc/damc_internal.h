@@ -194,6 +194,7 @@ struct GenWorkspace {   // carved out of the caller's workspace for a given B
   float* zbuf;               // [B][nz] fp32: staging copy of z for graph replays
   float* xbuf;               // [B][nc][H][W] fp32: staging copy of x for graph replays
   float* xhat_buf;           // [B][nc][H][W] fp32: G(z) of the last step inside a replayed graph (copied out to the caller)
+  float* sq_part;            // [B][score_parts] fp32: per-chain partial sums of (G(z) - x)^2 (damc_posterior_score)
   unsigned long long* seed_dev;   // {seed, chain0, step0} for replayed graphs
   void* base;
   size_t bytes;
@@ -234,14 +235,23 @@ int launch_stage_z(const float* z, void* zin, int B, int nz, int nz_p, int preci
 
 // fused last layer (scatter GEMM + col2im + tanh-likelihood gradient + K = 64 dgrad in one launch) -- gen_last.cu
 bool last_fused_supported(const GenPack* g);
+int last_fused_parts(const GenPack* g);   // blocks per image = partial sums per chain in score mode
+// sq_part == null: posterior step (forward, likelihood gradient, dgrad).  sq_part != null: score mode -- forward and the
+// per-block sums of (x_hat - x)^2 only ([B][last_fused_parts] floats)
 int launch_last_fused(const GenPack* g, const GenWorkspace& ws, int B, const float* x, float sigma, float* xhat, float* loss,
-                      cudaStream_t stream);
+                      float* sq_part, cudaStream_t stream);
 
 // generator driver -- gen_driver.cu
 int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
-                      float* xhat, float* loss, cudaStream_t stream);
+                      float* xhat, float* loss, cudaStream_t stream, float* sq_part = nullptr /* fused last layer: score mode */);
 float generator_grad_scale(const GenPack* g, float sigma);
 int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream);
+// G(z) with the per-chain squared residual against x reduced on the fly: sq_part [B][score_parts(g)] (eval consumers)
+int generator_score_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, cudaStream_t stream);
+int score_parts(const GenPack* g);
+int launch_sqerr(const float* xhat, const float* x, int B, int n, float* sq_part, cudaStream_t stream);
+int launch_ebm_score(const MlpPack* m, const float* z, int B, int nz, const float* sq_part, int nparts, float* score,
+                     float* sqerr, cudaStream_t stream);
 
 // ---- DAMC denoiser (Diffusion_UnetA, reference diffusion_net.py:463-533) ---------------------------------------------
 constexpr int DEN_LAYERS = 7;

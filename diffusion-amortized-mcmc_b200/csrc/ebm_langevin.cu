@@ -592,6 +592,82 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
                                gpart_scale, nz_if_no_ebm, stream, seed_ptr);
 }
 
+// Eval consumer (reference eval_anomaly_det.py:115-117): score_b = sum (G(z_b) - x_b)^2 + E(z_b) + |z_b|^2 / 2, the squared
+// error arriving as `nparts` partial sums per chain from the generator's score-mode forward.  E(z) is the forward half of
+// ebm_step_kernel (thread j owns hidden unit j of the 4 chains of the CTA, weights streamed from L2).
+__global__ void __launch_bounds__(256) ebm_score_kernel(const EbmStepArgs a, const float* __restrict__ sq_part, int nparts,
+                                                        float* __restrict__ score, float* __restrict__ sqerr) {
+  constexpr int CH = 4;
+  extern __shared__ __align__(16) float sm[];
+  const int nz = a.nz, ndf = a.ndf, tid = threadIdx.x;
+  float* zs = sm;               // [nz][CH]
+  float* a1s = zs + nz * CH;    // [ndf][CH]
+  __shared__ float red[8][CH];
+  const int c0 = blockIdx.x * CH;
+  const int nvalid = min(CH, a.B - c0);
+  for (int i = tid; i < nz * CH; i += blockDim.x) {
+    const int c = i / nz, k = i - c * nz;
+    zs[k * CH + c] = c < nvalid ? a.z[(size_t)(c0 + c) * nz + k] : 0.f;
+  }
+  __syncthreads();
+  float part[CH];   // per thread: its share of E(z_c) + |z_c|^2 / 2
+#pragma unroll
+  for (int c = 0; c < CH; ++c) part[c] = tid < nz ? 0.5f * zs[tid * CH + c] * zs[tid * CH + c] : 0.f;
+  if (a.use_ebm) {
+    float acc[CH];
+    if (tid < ndf) {
+      const float bb = a.b1[tid];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = bb;
+      stream_matvec<CH>(a.W1T + tid, ndf, nz, zs, acc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) a1s[tid * CH + c] = acc[c] > 0.f ? acc[c] : a.slope * acc[c];
+    }
+    __syncthreads();
+    if (tid < ndf) {
+      const float bb = a.b2[tid], w3 = a.w3[tid];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = bb;
+      stream_matvec<CH>(a.W2T + tid, ndf, ndf, a1s, acc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) part[c] = fmaf(w3, acc[c] > 0.f ? acc[c] : a.slope * acc[c], part[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float v = warp_sum(part[c]);
+    if ((tid & 31) == 0) red[tid >> 5][c] = v;
+  }
+  __syncthreads();
+  if (tid < nvalid) {
+    float e = a.use_ebm ? a.b3[0] : 0.f;
+    for (int w = 0; w < 8; ++w) e += red[w][tid];
+    float sq = 0.f;
+    for (int j = 0; j < nparts; ++j) sq += sq_part[(size_t)(c0 + tid) * nparts + j];   // ascending block order
+    if (sqerr) sqerr[c0 + tid] = sq;
+    if (score) score[c0 + tid] = sq + e;
+  }
+}
+
+int launch_ebm_score(const MlpPack* m, const float* z, int B, int nz, const float* sq_part, int nparts, float* score,
+                     float* sqerr, cudaStream_t stream) {
+  EbmStepArgs a{};
+  a.use_ebm = m != nullptr;
+  if (m) {
+    a.W1T = m->W1T; a.b1 = m->b1; a.W2T = m->W2T; a.b2 = m->b2; a.w3 = m->w3; a.b3 = m->b3;
+    a.nz = m->nz; a.ndf = m->ndf; a.slope = m->slope;
+  } else {
+    a.nz = nz; a.ndf = 0; a.slope = 1.f;
+  }
+  if (a.nz < 1 || a.nz > 256 || a.ndf > 256) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM score kernel: nz <= 256 and ndf <= 256 (nz=%d ndf=%d)", a.nz, a.ndf);
+  a.z = const_cast<float*>(z); a.B = B;
+  const size_t smem = sizeof(float) * 4 * ((size_t)a.nz + (size_t)a.ndf);
+  ebm_score_kernel<<<ceil_div(B, 4), 256, smem, stream>>>(a, sq_part, nparts, score, sqerr);
+  DAMC_CUDA(cudaGetLastError());
+  count_launch();
+  return DAMC_OK;
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
                                  const int* __restrict__ dirty) {
   if (gate_clean(dirty)) return;

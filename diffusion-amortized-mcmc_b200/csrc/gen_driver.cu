@@ -178,6 +178,7 @@ int plan_workspace(const GenPack* g, int B, void* base, GenWorkspace* ws) {
   ws->zbuf = (float*)take(sizeof(float) * (size_t)B * g->nz);
   ws->xbuf = (float*)take(sizeof(float) * (size_t)B * g->nc * g->H * g->W);
   ws->xhat_buf = (float*)take(sizeof(float) * (size_t)B * g->nc * g->H * g->W);
+  ws->sq_part = (float*)take(sizeof(float) * (size_t)B * score_parts(g));
   ws->seed_dev = (unsigned long long*)take(32);
   ws->base = base;
   ws->bytes = o;
@@ -206,7 +207,7 @@ static void up_fwd_taps(int cls, GemmPlan& p) {
 }
 
 int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, float sigma,
-                      float* xhat, float* loss, cudaStream_t stream) {
+                      float* xhat, float* loss, cudaStream_t stream, float* sq_part) {
   DAMC_TRY(launch_stage_z(z, ws.zin, B, g->nz, g->nz_p, g->precision, stream));
   count_launch();
   const int L = g->nlayers;
@@ -224,7 +225,7 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     e.sy = e.sx = y.type == L_UP ? 2 : 1;
     if (last && g->last_fused && x != nullptr) {   // forward + likelihood gradient + this layer's dgrad in one launch
       profile_mark(stream, true);
-      DAMC_TRY(launch_last_fused(g, ws, B, x, sigma, xhat, loss, stream));
+      DAMC_TRY(launch_last_fused(g, ws, B, x, sigma, xhat, loss, sq_part, stream));
       profile_mark(stream, false);
       count_launch();
       continue;
@@ -281,6 +282,19 @@ int generator_forward(const GenPack* g, const GenWorkspace& ws, const float* z, 
     }
   }
   return DAMC_OK;
+}
+
+int score_parts(const GenPack* g) { return g->last_fused ? last_fused_parts(g) : 1; }
+
+// Eval consumers (reference eval_anomaly_det.py:114-117, eval_gen_recon.py:192-194): G(z) and sum (G(z) - x)^2 per chain.
+// 16-bit tensor-core modes: the fused last-layer kernel in score mode reduces the residual where x_hat is formed (x_hat never
+// reaches HBM).  Other modes: the ordinary forward into the workspace, then a per-chain reduction kernel.
+int generator_score_forward(const GenPack* g, const GenWorkspace& ws, const float* z, int B, const float* x, cudaStream_t stream) {
+  if (!g->last_fused) {
+    DAMC_TRY(generator_forward(g, ws, z, B, nullptr, 1.0f, ws.xhat_buf, nullptr, stream));
+    return launch_sqerr(ws.xhat_buf, x, B, g->nc * g->H * g->W, ws.sq_part, stream);
+  }
+  return generator_forward(g, ws, z, B, x, 1.0f, nullptr, nullptr, stream, ws.sq_part);
 }
 
 int generator_dgrad(const GenPack* g, const GenWorkspace& ws, int B, cudaStream_t stream) {

@@ -61,6 +61,11 @@ struct LastParams {
   const uint32_t* maskbits;    // sign bits of a (NHWC element order), 1 = pre-activation > 0
   void* gout;                  // dU/da, operand type
   int planar_out;
+  // score mode (damc_posterior_score): forward + squared residual only -- no gradient image, no dgrad; every block writes
+  // the sum of (x_hat - x)^2 over the output rows it owns to sq_part[b * nblk_img + block-in-image]
+  int do_dgrad;
+  float* sq_part;
+  uint32_t off_red;
 };
 
 // 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
@@ -206,7 +211,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 2) {
     // ===================== dgrad-GEMM issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && P.do_dgrad) {
       mbar_wait(bar_w, 0u);
       tc_fence_after();
       int jt = 0, jc = 0;
@@ -357,7 +362,8 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // x arrives in smem by bulk copies issued at the START of the block (a dependent global load per pixel would expose a
       // loaded-DRAM round trip per iteration, ~3 k clocks each); blocks whose rows do not fit take it in several chunks.
       const int own0 = L.r0 * S, own1 = L.r1 * S;
-      LF_T(dbg2, mbar_wait(bar_gempty, ((uint32_t)nb & 1u) ^ 1u));   // the E group has gathered the previous block's gradient image
+      if (P.do_dgrad) LF_T(dbg2, mbar_wait(bar_gempty, ((uint32_t)nb & 1u) ^ 1u));   // the E group has gathered the previous block's gradient image
+      float sq_acc = 0.f;
       const uint32_t tp2 = P.debug ? (uint32_t)clock() : 0u;
       for (int lr0 = 0; lr0 < L.n_need; lr0 += P.xr) {
         const int lr1 = min(L.n_need, lr0 + P.xr);
@@ -386,16 +392,27 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (P.xhat != nullptr && own) P.xhat[(((size_t)L.b * NC + c) * P.Ho + oy) * P.Wo + ox] = xh;
               const float rr = xh - x_s[(c * P.xr + (oy - cy0)) * P.Wo + ox];
               g[c] = rr * gmul * (1.f - xh * xh);
-              if (own) loss_acc += 0.5f * P.inv_sigma2 * rr * rr;
+              if (own) { loss_acc += 0.5f * P.inv_sigma2 * rr * rr; sq_acc = fmaf(rr, rr, sq_acc); }
             }
           }
-          const uint32_t w0 = pack2(P.op_fp16, g[0], g[1]), w1 = pack2(P.op_fp16, g[2], g[3]);
-          *reinterpret_cast<uint2*>(g_s + (size_t)lrow * gpitch + (size_t)(ox + 1) * 8) = make_uint2(w0, w1);
+          if (P.do_dgrad) {
+            const uint32_t w0 = pack2(P.op_fp16, g[0], g[1]), w1 = pack2(P.op_fp16, g[2], g[3]);
+            *reinterpret_cast<uint2*>(g_s + (size_t)lrow * gpitch + (size_t)(ox + 1) * 8) = make_uint2(w0, w1);
+          }
         }
       }
       if (P.debug) dbg3 += (uint32_t)clock() - tp2;
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_gfull);   // release: this warp's gradient pixels are visible to the E group
+      if (P.do_dgrad) {
+        if (lane == 0) mbar_arrive(bar_gfull);   // release: this warp's gradient pixels are visible to the E group
+      } else if (P.sq_part != nullptr) {
+        // fixed-order reduction (lanes by shuffle tree, then warps 0..3): the per-chain squared error is bit-reproducible
+        sq_acc = warp_sum(sq_acc);
+        float* red = reinterpret_cast<float*>(gen_base + P.off_red);
+        if (lane == 0) red[q] = sq_acc;
+        named_bar_sync(1, 128);
+        if (sid == 0) P.sq_part[blk] = ((red[0] + red[1]) + red[2]) + red[3];
+      }
       named_bar_sync(1, 128);                  // every pre-activation is re-initialised before the next block accumulates
     }
     if (P.debug && blockIdx.x == 0 && sid == 0)
@@ -404,7 +421,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       loss_acc = warp_sum(loss_acc);
       if (lane == 0 && loss_acc != 0.f) atomicAdd(P.loss, loss_acc);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && P.do_dgrad) {
     // ===================== E group: operand gather (P3a) and the masked dgrad epilogue (P3b) =====================
     const int q = warp & 3, half = (warp - 8) >> 2, eid = threadIdx.x - 256;
     int jb = 0, jc = 0, nb = 0;
@@ -579,7 +596,7 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   if (P.Np_sc > 64 || P.Np_sc != (y.k * y.k * y.cout + 15) / 16 * 16) return false;
   const int halo_rows = same ? 2 : 1;
   const size_t wbytes = (size_t)P.kb_sc * P.Np_sc * 128 + (size_t)y.cin * 128;
-  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 16) + 64 + 1024;
+  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 16) + 96 + 1024;
   const size_t cap = 227 * 1024;
   auto need_rows = [&](int Rt) { return (Rt * P.Ht - 1) * y.stride - y.pad + y.k - 1 - (0 * y.stride - y.pad) + 1; };
   if (P.nchunks > LF_MAX_CHUNKS) return false;
@@ -619,6 +636,7 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   P.off_out = off; off += (uint32_t)align_up((size_t)P.out_floats * 4, 16);
   P.off_g = off; off += (uint32_t)P.g_bytes;
   P.off_x = off; off += (uint32_t)align_up((size_t)y.cout * P.xr * y.Wout * 4, 16);
+  P.off_red = (uint32_t)align_up(off, 16); off = P.off_red + 16;
   P.off_bar = (uint32_t)align_up(off, 8);
   const size_t total = P.off_bar + 8 * (2 * LF_MAX_STAGES + 16) + 16 + 1024;
   if (total > cap) return false;
@@ -638,8 +656,13 @@ bool last_fused_supported(const GenPack* g) {
   return !(e && e[0] == '0') && last_plan(g, 1, &pl);
 }
 
+int last_fused_parts(const GenPack* g) {
+  LastPlan pl;
+  return last_plan(g, 1, &pl) ? pl.P.nblk_img : 1;
+}
+
 int launch_last_fused(const GenPack* g, const GenWorkspace& ws, int B, const float* x, float sigma, float* xhat, float* loss,
-                      cudaStream_t stream) {
+                      float* sq_part, cudaStream_t stream) {
   LastPlan pl;
   if (!last_plan(g, B, &pl)) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "fused last layer: unsupported shape");
   const int L = g->nlayers;
@@ -652,6 +675,8 @@ int launch_last_fused(const GenPack* g, const GenWorkspace& ws, int B, const flo
   P.maskbits = ws.mask[L - 2];
   P.gout = ws.grad[L - 2];
   P.planar_out = g->layers[L - 2].type == L_UP ? 1 : 0;
+  P.do_dgrad = sq_part == nullptr ? 1 : 0;
+  P.sq_part = sq_part;
   { const char* e = getenv("DAMC_LAST_DEBUG"); P.debug = (e && e[0] == '1') ? 1 : 0; }
   CUtensorMap tmA, tmWsc, tmWdg;
   DAMC_TRY(tc_encode_act(&tmA, g->precision, ws.act[L - 2], y.cin, y.Win, y.Hin, B, P.Ht));

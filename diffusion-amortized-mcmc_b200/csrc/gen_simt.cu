@@ -441,6 +441,33 @@ int launch_last_finish(const GenLayer& y, int precision, const float* Y, int B, 
   return go(last_finish_kernel<float, 0, 0>);
 }
 
+// sum over one chain's image of (x_hat - x)^2, fixed reduction order (thread-strided partial sums, shuffle tree, warps in order)
+__global__ void __launch_bounds__(256) sqerr_kernel(const float* __restrict__ xhat, const float* __restrict__ x, int n,
+                                                    float* __restrict__ sq_part) {
+  const size_t base = (size_t)blockIdx.x * n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float r = xhat[base + i] - __ldg(x + base + i);
+    acc = fmaf(r, r, acc);
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    sq_part[blockIdx.x] = t;
+  }
+}
+
+int launch_sqerr(const float* xhat, const float* x, int B, int n, float* sq_part, cudaStream_t stream) {
+  sqerr_kernel<<<B, 256, 0, stream>>>(xhat, x, n, sq_part);
+  DAMC_CUDA(cudaGetLastError());
+  count_launch();
+  return DAMC_OK;
+}
+
 template <typename T>
 __global__ void stage_z_kernel(const float* __restrict__ z, T* __restrict__ zin, int B, int nz, int nz_p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -345,19 +345,42 @@ def gen_samples_with_diffusion_prior(b, device, netQ, netG, *, precision=None):
     return x, zk_prior
 
 
+def posterior_score(x, z, netG, netE=None, *, precision=None):
+    """(score [B], sqerr [B]) of the eval scripts in ONE library pass: sqerr_b = |G(z_b) - x_b|^2 is reduced where x_hat is
+    formed (no x_hat tensor, no separate netG forward), score_b = sqerr_b + E(z_b) + |z_b|^2/2 (no torch netE call).
+    Reference: eval_anomaly_det.py:114-117, eval_gen_recon.py:192-193."""
+    zd, xs = _f32_cuda(z, "z"), _f32_cuda(x, "x")
+    gh = pack_generator(netG, precision)
+    eh = pack_ebm(netE) if netE is not None else None
+    nz, nc, H, W = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(lib().damc_generator_shape(gh.ptr, C.byref(nz), C.byref(nc), C.byref(H), C.byref(W)))
+    if zd.dim() != 2 or zd.shape[1] != nz.value or tuple(xs.shape) != (zd.shape[0], nc.value, H.value, W.value) or \
+            xs.device != zd.device:
+        raise RuntimeError(f"shape mismatch: z {tuple(zd.shape)}, x {tuple(xs.shape)}, generator nz={nz.value} "
+                           f"-> [{nc.value},{H.value},{W.value}]")
+    B = zd.shape[0]
+    score = torch.empty(B, dtype=torch.float32, device=zd.device)
+    sqerr = torch.empty(B, dtype=torch.float32, device=zd.device)
+    nbytes = lib().damc_generator_workspace_bytes(gh.ptr, B)
+    ws = _workspace(zd.device, nbytes)
+    with torch.cuda.device(zd.device):
+        check(lib().damc_posterior_score(gh.ptr, eh.ptr if eh is not None else None, C.c_void_p(zd.data_ptr()),
+                                         C.c_void_p(xs.data_ptr()), B, C.c_void_p(score.data_ptr()),
+                                         C.c_void_p(sqerr.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes,
+                                         _stream(zd.device)), "damc_posterior_score")
+    return score, sqerr
+
+
 def recon_mse(x, z, netG, *, precision=None):
     """sum_b mean_pixels (G(z_b) - x_b)^2 -- the quantity accumulated at eval_gen_recon.py:192-194 /
-    train_gen_recon.py:340-343 after the noise-free Langevin refinement."""
-    x_hat = generator_forward(netG, z, precision)
-    return torch.mean((x_hat - x) ** 2, dim=[1, 2, 3]).sum()
+    train_gen_recon.py:340-343 after the noise-free Langevin refinement (fused residual reduction, see posterior_score)."""
+    _, sqerr = posterior_score(x, z, netG, None, precision=precision)
+    return (sqerr / float(x[0].numel())).sum()
 
 
 def anomaly_score(x, z, netG, netE, *, precision=None):
-    """Per-sample score |G(z)-x|^2 + E(z) + |z|^2/2 of eval_anomaly_det.py:114-119 (G through the packed kernels)."""
-    x_hat = generator_forward(netG, z, precision)
-    with torch.no_grad():
-        s_hat = netE(z)
-    return torch.sum((x_hat - x) ** 2, dim=[1, 2, 3]) + s_hat + 0.5 * torch.sum(z ** 2, dim=-1)
+    """Per-sample score |G(z)-x|^2 + E(z) + |z|^2/2 of eval_anomaly_det.py:114-119, in one library pass."""
+    return posterior_score(x, z, netG, netE, precision=precision)[0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -74,6 +74,15 @@ size_t damc_generator_workspace_bytes(const damc_handle* gen, int B);
 int damc_generator_forward(const damc_handle* gen, const float* z, float* x_hat, int B, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- eval consumers right after the posterior sampler (reference eval_anomaly_det.py:114-119, eval_gen_recon.py:192-194) --
+ * One pass: x_hat = G(z) is formed tile by tile and reduced against x where it is produced (it never reaches HBM in the
+ * 16-bit tensor-core modes); E(z) and |z|^2/2 come from one small kernel -- no separate netG / netE forward.
+ *   sqerr[b] = sum_{c,h,w} (G(z_b) - x_b)^2                 (recon MSE = sqerr / (nc H W), eval_gen_recon.py:193)
+ *   score[b] = sqerr[b] + E(z_b) + |z_b|^2 / 2              (anomaly score, eval_anomaly_det.py:117; E = 0 when ebm is NULL)
+ * score / sqerr: [B] device pointers, either may be NULL.  Same workspace as damc_posterior_langevin.                 */
+int damc_posterior_score(const damc_handle* gen, const damc_handle* ebm, const float* z, const float* x, int B,
+                         float* score, float* sqerr, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- prior Langevin  (replaces sample_langevin_prior_z, reference src/MCMC.py:27-46) --------------------------
  * z [B,nz] is updated IN PLACE:  z <- z - step^2/2 (dE/dz + z) + step * eps  for K steps in ONE launch.
  * noise : NULL -> Philox4x32-10 keyed by (seed, chain0 + row, step0 + i); else injected normals [K,B,nz].

@@ -101,3 +101,47 @@ def test_fused_last_layer_is_deterministic_and_batch_invariant(dev):
     assert torch.isfinite(full).all()
     assert torch.equal(full, again)
     assert torch.equal(full[:9], few)
+
+
+# ---- eval consumers: fused score pass (damc_posterior_score) ---------------------------------------------------------------
+SCORE_CASES = [("cifar10", 128, 128, 3, 5, 0.1), ("svhn", 100, 64, 3, 6, 0.1), ("mnist", 8, 128, 1, 9, 1.0),
+               ("celebaHQ", 128, 64, 3, 2, 1.0)]
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("tf32", 2e-3), ("fp16", 2e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dataset,nz,ngf,nc,B,sigma", SCORE_CASES)
+def test_posterior_score_matches_oracle(dataset, nz, ngf, nc, B, sigma, prec, tol, dev):
+    """score_b = |G(z_b) - x_b|^2 + E(z_b) + |z_b|^2/2 and sqerr_b from ONE library pass against the reference formula
+    (eval_anomaly_det.py:114-117, eval_gen_recon.py:192-193) evaluated by the fp64 oracle: 1e-5 in fp32, 2e-2 with bf16
+    operands.  The 16-bit modes run the fused last-layer kernel in score mode (CelebA-HQ: several row blocks per image, so
+    several partial sums per chain); fp32 / tf32 the ordinary forward plus the per-chain reduction kernel."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, _ = synth.synth_problem(layers, nz, B, 1, sigma, seed=9, gain=0.0)
+    G, E = dn._netG(dataset, nz, ngf, nc), dn._netE(nz)
+    G.load_state_dict(gsd)
+    E.load_state_dict(esd)
+    G, E = G.to(dev), E.to(dev)
+    gen, ebm = synth.gen_list_from_state(gsd, layers, torch.float64), synth.ebm_list_from_state(esd, torch.float64)
+    xh = O.gen_forward(gen, z0.double())
+    sq_ref = ((xh - x.double()) ** 2).sum((1, 2, 3))
+    score_ref = sq_ref + O.ebm_forward(ebm, z0.double()) + 0.5 * (z0.double() ** 2).sum(1)
+    n0 = MCMC.lib().damc_launch_count()
+    score, sqerr = MCMC.posterior_score(x.to(dev), z0.to(dev), G, E, precision=prec)
+    torch.cuda.synchronize()
+    launches = MCMC.lib().damc_launch_count() - n0
+    e_sq = float(((sqerr.cpu().double() - sq_ref).abs() / sq_ref.abs()).max())
+    e_sc = float(((score.cpu().double() - score_ref).abs() / score_ref.abs()).max())
+    print(f"{dataset} [{prec}]: sqerr rel err {e_sq:.3e}  score rel err {e_sc:.3e}  ({launches} launches)")
+    assert e_sq < tol and e_sc < tol
+    # 16-bit modes: stage_z + ONE launch per generator layer (the last one reduces the residual itself) + the score kernel --
+    # no separate generator forward, no x_hat tensor, no torch netE
+    if prec in ("bf16", "fp16"):
+        assert launches == len(layers) + 2, launches
+    again, _ = MCMC.posterior_score(x.to(dev), z0.to(dev), G, E, precision=prec)
+    assert torch.equal(score, again)   # fixed-order reductions
+    # the wrappers the eval scripts call
+    assert torch.equal(MCMC.anomaly_score(x.to(dev), z0.to(dev), G, E, precision=prec), score)
+    mse = MCMC.recon_mse(x.to(dev), z0.to(dev), G, precision=prec)
+    mse_ref = ((xh - x.double()) ** 2).mean((1, 2, 3)).sum()
+    assert abs(float(mse) - float(mse_ref)) < tol * float(mse_ref)
