@@ -32,12 +32,26 @@ class TrainConfig:  # defaults = train_gen_recon.py:383-402
 
 
 def _step(loss, params, opt, cfg, group):
+    if isinstance(opt, parallel.FlatAdam):
+        # flat gradient buffer: buckets are all-reduced from backward hooks while backward runs; clip + Adam(W) in one fused pass
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return
     opt.zero_grad()
     loss.backward()
     if dist.is_available() and dist.is_initialized():
         parallel.allreduce_mean_grads(params, group)
     torch.nn.utils.clip_grad_norm_(params, max_norm=cfg.max_norm)
     opt.step()
+
+
+def make_fused_optimizers(G, E, Q, cfg, g_lr=2e-4, e_lr=1e-4, q_lr=2e-4, group=None, bucket_bytes=32 << 20):
+    """The reference's three optimisers (train_gen_recon.py:152-154: Adam / Adam / AdamW(weight_decay=1e-4), betas (0.5, 0.999))
+    as FlatAdam instances with the clip threshold folded in.  Returns (G_opt, E_opt, Q_opt) in training_iteration's order."""
+    mk = lambda net, lr, wd, dec: parallel.FlatAdam(net.parameters(), lr=lr, betas=(0.5, 0.999), weight_decay=wd, decoupled=dec,
+                                                    max_norm=cfg.max_norm, group=group, bucket_bytes=bucket_bytes)
+    return mk(G, g_lr, 0.0, False), mk(E, e_lr, 0.0, False), mk(Q, q_lr, 1e-4, True)
 
 
 def training_iteration(x, G, E, Q, Q_dummy, G_opt, E_opt, Q_opt, cfg=TrainConfig(), group=None, chain0=None):

@@ -175,6 +175,18 @@ long long damc_graph_replays(const damc_handle* gen);
 int damc_profile_enable(int on);
 int damc_profile_collect(double* gemm_ms, long long* gemm_launches);
 
+/* ---- optimiser half of the training step that calls the samplers (reference train_gen_recon.py:218-219, :229-230, :239-240:
+ * clip_grad_norm_(max_norm) followed by Adam / AdamW .step(), optimisers of :152-154) over ONE flat fp32 buffer ---------
+ * grads are read as grad_scale * g (grad_scale = 1 / world_size after a SUM all-reduce of the flat buffer), their global L2
+ * norm is reduced in a fixed order, and the update is applied to the listed element ranges only (parameters that received
+ * no gradient this step are skipped, as torch skips .grad = None), each with its own 1-based step count.
+ *   decoupled = 1: AdamW (p *= 1 - lr wd), 0: Adam (g += wd p).  max_norm <= 0: no clipping.
+ *   scratch: >= 1025 floats of device memory; scratch[1024] receives the total gradient norm (what clip_grad_norm_ returns). */
+int damc_fused_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n_total, int nranges,
+                         const unsigned long long* range_begin, const unsigned long long* range_count, const int* range_step,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, float max_norm,
+                         float grad_scale, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

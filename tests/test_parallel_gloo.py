@@ -62,3 +62,60 @@ def _worker(rank, world, port, n):
 @pytest.mark.parametrize("n", [10, 7])
 def test_two_rank_sharding_and_grad_average(n):
     mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+class _TwoHead(torch.nn.Module):
+    """fc1 -> (head_a | head_b): a loss through head_a alone leaves head_b without a gradient (like Q.prior_emb in
+    calculate_loss with an image batch)."""
+
+    def __init__(self):
+        super().__init__()
+        self.fc1, self.head_a, self.head_b = torch.nn.Linear(16, 32), torch.nn.Linear(32, 3), torch.nn.Linear(32, 5)
+        with torch.no_grad():
+            for i, p in enumerate(self.parameters()):
+                p.copy_(torch.linspace(-0.5, 0.5 + 0.1 * i, p.numel()).view_as(p))
+
+    def forward(self, z):
+        return self.head_a(torch.tanh(self.fc1(z)))
+
+
+def _reducer_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        z = torch.randn(12, 16)
+        ref, net = _TwoHead(), _TwoHead()
+        red = parallel.FlatGradReducer(net.parameters(), bucket_bytes=256)   # several small buckets
+        assert len(red.buckets) > 2 and red.world == world
+        for step in range(3):
+            ref.zero_grad()
+            ref(z).pow(2).sum(1).mean().backward()
+            if step == 1:   # an outside zero_grad(set_to_none=True) detaches the views: the hooks must fold the fresh grads back
+                for p in net.parameters():
+                    p.grad = None
+                red._pending = [c for _, _, c in red.buckets]
+                red._launched = [False] * len(red.buckets)
+                red.fired = [False] * len(red.params)
+                red.flat_grad.zero_()
+            else:
+                red.zero_grad()
+            zl, _ = parallel.shard(z, rank, world)
+            net(zl).pow(2).sum(1).mean().backward()
+            launched_in_backward = sum(red._launched)
+            red.finish()
+            assert launched_in_backward >= 1          # complete buckets went out from the hooks, during backward
+            assert all(red._launched)
+            for (name, a), b in zip(net.named_parameters(), ref.parameters()):
+                fired = red.fired[[id(q) for q in red.params].index(id(a))]
+                if name.startswith("head_b"):
+                    assert not fired and (a.grad is None or float(a.grad.abs().max()) == 0.0)
+                    continue
+                assert fired and a.grad.data_ptr() >= red.flat_grad.data_ptr()   # still a view of the flat buffer
+                assert torch.allclose(a.grad * red.grad_scale(), b.grad, atol=1e-6), (name, (a.grad * red.grad_scale() - b.grad).abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_reducer_overlapped_buckets_two_ranks():
+    mp.spawn(_reducer_worker, args=(2, _free_port()), nprocs=2, join=True)
