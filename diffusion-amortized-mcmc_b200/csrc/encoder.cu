@@ -16,6 +16,10 @@
 //     the pixels, then re-reads the slab (L2-hot) and writes the normalised activation in the operand type, already in
 //     the layout the next GEMM's TMA boxes want (4 parity planes, or flat NHWC before the last layer).
 //     The conv bias of a normalised layer cancels exactly ((x+b) - mean(x+b) = x - mean(x)) and is not added.
+//   * odd-sized maps (Encoder_mnist :374-413: 28 -> 14 -> 7 -> 3 -> 1): a k4-s2-p1 convolution of an H x W map equals the
+//     same convolution of the map zero-padded to even size, restricted to the first floor((H-2)/2)+1 outputs.  So the
+//     parity planes are ceil(H/2) x ceil(W/2) with zeros at the pixels that do not exist (the buffer is cleared per call),
+//     the GEMM runs on that padded grid, and the normalisation that follows reads the real outputs only.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -31,6 +35,7 @@ enum EncType { ENC_FIRST = 0, ENC_DOWN = 1, ENC_LAST = 2 };
 
 struct EncLayer {
   int type, cin, cout, k, Hin, Win, Hout, Wout;
+  int Hg, Wg;   // pixel grid of the layer's raw fp32 output: = Hout x Wout, or ceil(Hin/2) x ceil(Win/2) for a down layer on an odd map
   damc_conv_layer src;
   void* w_simt = nullptr;   // [ntaps*Cs][N]  (CUDA-core engine)
   void* w_tc = nullptr;     // [ntaps][N][Cs] (tcgen05 engine)
@@ -60,14 +65,15 @@ static EncWs enc_ws(const EncPack* e, int B, void* base) {
   size_t raw = 0;
   for (int l = 0; l + 1 < e->nlayers; ++l) {
     const EncLayer& y = e->layers[l];
-    raw = std::max(raw, sizeof(float) * (size_t)B * y.Hout * y.Wout * y.cout);
+    raw = std::max(raw, sizeof(float) * (size_t)B * y.Hg * y.Wg * y.cout);
   }
   w.raw = (float*)take(raw);
   w.act.assign(e->nlayers - 1, nullptr);
   const size_t es = elem_size(e->precision);
   for (int l = 0; l + 1 < e->nlayers; ++l) {
     const EncLayer& y = e->layers[l];
-    w.act[l] = take(es * (size_t)B * y.Hout * y.Wout * y.cout);
+    const bool planar = e->layers[l + 1].type == ENC_DOWN;   // 4 parity planes of ceil(H/2) x ceil(W/2) pixels
+    w.act[l] = take(es * (size_t)B * y.cout * (planar ? 4 * (size_t)((y.Hout + 1) / 2) * ((y.Wout + 1) / 2) : (size_t)y.Hout * y.Wout));
   }
   w.bytes = o;
   return w;
@@ -115,15 +121,17 @@ __global__ void __launch_bounds__(256) enc_first_conv_kernel(const float* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) enc_instnorm_kernel(const float* __restrict__ raw, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ out, int B,
-                                                           int H, int W, int C, int planar, float eps, float slope) {
+                                                           int H, int W, int Hg, int Wg, int C, int planar, float eps,
+                                                           float slope) {
   __shared__ double red[2][8][32];
   __shared__ float stat[2][32];
   const int c = threadIdx.x & 31, pl = threadIdx.x >> 5, c0 = blockIdx.y * 32, b = blockIdx.x;   // images on grid.x (no 65 535 cap)
-  const int HW = H * W;
-  const float* src = raw + (size_t)b * HW * C + c0 + c;
+  const int HW = H * W;   // real pixels; the raw tensor is [B][Hg][Wg][C] with Hg >= H, Wg >= W (padded grid of an odd map)
+  const float* src = raw + (size_t)b * Hg * Wg * C + c0 + c;
+  auto raw_pix = [&](int p) { return Wg == W ? p : (p / W) * Wg + (p % W); };
   float s = 0.f, s2 = 0.f;
   for (int p = pl; p < HW; p += 8) {
-    const float v = src[(size_t)p * C];
+    const float v = src[(size_t)raw_pix(p) * C];
     s += v;
     s2 = fmaf(v, v, s2);
   }
@@ -144,9 +152,9 @@ __global__ void __launch_bounds__(256) enc_instnorm_kernel(const float* __restri
   }
   __syncthreads();
   const float sc = stat[0][c], sh = stat[1][c];
-  const int Hh = H >> 1, Wh = W >> 1;
+  const int Hh = (H + 1) >> 1, Wh = (W + 1) >> 1;
   for (int p = pl; p < HW; p += 8) {
-    float v = fmaf(src[(size_t)p * C], sc, sh);
+    float v = fmaf(src[(size_t)raw_pix(p) * C], sc, sh);
     v = v > 0.f ? v : slope * v;
     size_t o;
     if (planar) {
@@ -198,8 +206,10 @@ int EncPack::refill(cudaStream_t stream, const int* dirty) {
 template <typename T>
 static int launch_instnorm(const EncPack* e, const EncLayer& y, const float* raw, void* out, int B, int planar,
                            cudaStream_t s) {
+  if (planar && ((y.Hout | y.Wout) & 1))   // odd map: the parity planes keep zeros where no pixel exists
+    DAMC_CUDA(cudaMemsetAsync(out, 0, sizeof(T) * 4 * (size_t)B * ((y.Hout + 1) / 2) * ((y.Wout + 1) / 2) * y.cout, s));
   enc_instnorm_kernel<T><<<dim3(B, y.cout / 32), 256, 0, s>>>(raw, y.src.in_weight, y.src.in_bias, (T*)out, B, y.Hout,
-                                                               y.Wout, y.cout, planar, e->eps, e->slope);
+                                                               y.Wout, y.Hg, y.Wg, y.cout, planar, e->eps, e->slope);
   DAMC_CUDA(cudaGetLastError());
   count_launch();
   return DAMC_OK;
@@ -223,8 +233,8 @@ static int encoder_run(const EncPack* e, const EncWs& w, const float* x, float* 
       p.ksplit = 1;
       p.W = y.w_simt; p.Wtc = y.w_tc;
       if (y.type == ENC_DOWN) {   // out[y] = sum_kh in[2y - 1 + kh] W[kh]: parity plane (kh+1)&1, shift -1/0/0/+1
-        p.Hm = y.Hout; p.Wm = y.Wout; p.Cs = y.cin; p.ntaps = 16;
-        p.plane_stride = (long long)B * y.Hout * y.Wout * y.cin;
+        p.Hm = y.Hg; p.Wm = y.Wg; p.Cs = y.cin; p.ntaps = 16;   // the plane grid (padded for odd maps)
+        p.plane_stride = (long long)B * y.Hg * y.Wg * y.cin;
         for (int kh = 0; kh < 4; ++kh)
           for (int kw = 0; kw < 4; ++kw) {
             Tap& t = p.taps[kh * 4 + kw];
@@ -284,16 +294,17 @@ extern "C" int damc_pack_encoder(damc_handle** out, int nlayers, const damc_conv
     y.src = s; y.cin = s.cin; y.cout = s.cout; y.k = s.k; y.Hin = H; y.Win = W;
     if (i == 0) {
       if (s.k != 3 || s.stride != 1 || s.pad != 1 || s.cin > 4 || s.cout % 64) return fail("first layer must be Conv2d(nc<=4, 64n, 3, 1, 1)", i);
-      y.type = ENC_FIRST; y.Hout = H; y.Wout = W;
+      y.type = ENC_FIRST; y.Hout = H; y.Wout = W; y.Hg = H; y.Wg = W;
     } else if (i < nlayers - 1) {
       if (s.k != 4 || s.stride != 2 || s.pad != 1) return fail("inner layers must be Conv2d(k=4, s=2, p=1)", i);
-      if ((H & 1) || (W & 1)) return fail("k4-s2-p1 layer on an odd-sized map (e.g. the 28x28 MNIST encoder) is not supported; keep that encoder in PyTorch", i);
+      if (H < 2 || W < 2) return fail("k4-s2-p1 layer needs a map of at least 2 x 2", i);
       if (s.cin % 64 || s.cout % 64) return fail("channel counts must be multiples of 64", i);
-      y.type = ENC_DOWN; y.Hout = H / 2; y.Wout = W / 2;
+      y.type = ENC_DOWN; y.Hout = (H - 2) / 2 + 1; y.Wout = (W - 2) / 2 + 1;   // = H/2 for even H
+      y.Hg = (H + 1) / 2; y.Wg = (W + 1) / 2;
     } else {
       if (s.stride != 1 || s.pad != 0 || s.k != H || s.k != W) return fail("last layer must reduce the k x k map to 1 x 1 (stride 1, padding 0)", i);
       if ((s.k * s.k * s.cin) % 64 || s.cout % 16) return fail("last layer: k*k*cin must be a multiple of 64 and nemb of 16", i);
-      y.type = ENC_LAST; y.Hout = 1; y.Wout = 1;
+      y.type = ENC_LAST; y.Hout = 1; y.Wout = 1; y.Hg = 1; y.Wg = 1;
     }
     if (i < nlayers - 1 && (!s.in_weight || !s.in_bias)) return fail("InstanceNorm2d(affine=True) parameters are required", i);
     H = y.Hout; W = y.Wout;

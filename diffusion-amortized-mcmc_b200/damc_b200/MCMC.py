@@ -492,7 +492,8 @@ def pack_encoder(enc, height, width, precision):
 def encoder_forward(enc, x, precision=None):
     """xemb = enc(x) [B, nemb] through libdamc_b200: direct first convolution, k4-s2-p1 convolutions as the generator
     engines' stride-2 GEMMs (tcgen05 for 'bf16' / 'fp16', CUDA-core for 'fp32'), fused InstanceNorm + LeakyReLU kernels.
-    Raises for encoders outside that family (e.g. the 28x28 MNIST encoder, odd-sized maps)."""
+    Odd-sized maps (the 28x28 MNIST encoder: 28 -> 14 -> 7 -> 3 -> 1) are handled on zero-padded parity planes.
+    Raises for encoders outside that family."""
     precision = _den_prec(precision)
     xs = _f32_cuda(x, "x")
     if xs.dim() != 4:
@@ -520,8 +521,8 @@ def _encoder_on_library(enc, x):
         if i == 0:
             ok = (k, s, p) == (3, 1, 1) and c.in_channels <= 4 and c.out_channels % 64 == 0
         elif i < len(pairs) - 1:
-            ok = (k, s, p) == (4, 2, 1) and H % 2 == 0 and W % 2 == 0 and c.in_channels % 64 == 0 and c.out_channels % 64 == 0
-            H, W = H // 2, W // 2
+            ok = (k, s, p) == (4, 2, 1) and H >= 2 and W >= 2 and c.in_channels % 64 == 0 and c.out_channels % 64 == 0
+            H, W = (H - 2) // 2 + 1, (W - 2) // 2 + 1   # odd maps (MNIST: 7 -> 3) run on zero-padded parity planes
         else:
             ok = s == 1 and p == 0 and k == H == W and (k * k * c.in_channels) % 64 == 0 and c.out_channels % 16 == 0
         if not ok:
@@ -539,7 +540,7 @@ def logsnr_table(T, logsnr_min, logsnr_max):
 
 
 def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init=None, seed=None, chain0=0,
-                precision=None, xemb=None):
+                precision=None, xemb=None, encoder_precision=None):
     """DAMC ancestral sampler: z_T ~ N(0,I), T reverse steps of the latent denoiser, returns z_0 [b,nz].
     The image encoder / prior embedding run once in PyTorch; the T-step loop runs in libdamc_b200.
     noise: optional [T-1,b,nz] injected normals; z_init: optional z_T (otherwise torch.randn as the reference)."""
@@ -554,8 +555,11 @@ def damc_sample(Q, x=None, b=None, device=None, cond_w=-1, noise=None, *, z_init
             b, device = len(x), x.device
             # tensor-core modes: the encoder runs on the library too (same operand precision as the denoiser GEMMs);
             # the fp32 parity mode keeps torch's fp32 convolutions, as do encoders outside the supported family
-            if prec != _lib.PREC_FP32 and x.is_cuda and _encoder_on_library(Q.encoder, x):
-                xemb = encoder_forward(Q.encoder, x, precision or DEFAULT_DENOISER_PRECISION)
+            # (encoder_precision: run the encoder on the library whatever the denoiser mode -- e.g. MNIST, whose nz = 8
+            #  denoiser is below the tensor-core granularity and runs in the fp32 persistent kernel)
+            enc_prec = encoder_precision or (None if prec == _lib.PREC_FP32 else (precision or DEFAULT_DENOISER_PRECISION))
+            if enc_prec is not None and x.is_cuda and _encoder_on_library(Q.encoder, x):
+                xemb = encoder_forward(Q.encoder, x, enc_prec)
             else:
                 xemb = Q.encoder(x)
         else:

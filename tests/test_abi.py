@@ -90,7 +90,7 @@ def test_encoder_family_detection(built_lib):
     assert MCMC._encoder_on_library(dn.Encoder("cifar10", nc=3, nemb=1024, nif=64), torch.zeros(1, 3, 32, 32))
     assert MCMC._encoder_on_library(dn.Encoder("celeba64", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 64, 64))
     assert MCMC._encoder_on_library(dn.Encoder("celebaHQ", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 256, 256))
-    assert not MCMC._encoder_on_library(dn.Encoder("mnist", nc=1, nemb=128, nif=64), torch.zeros(1, 1, 28, 28))
+    assert MCMC._encoder_on_library(dn.Encoder("mnist", nc=1, nemb=128, nif=64), torch.zeros(1, 1, 28, 28))   # odd maps: padded planes
     assert not MCMC._encoder_on_library(dn.Encoder("cifar10", nc=3, nemb=128, nif=64), torch.zeros(1, 3, 48, 48))
     enc = dn.Encoder("cifar10", nc=3, nemb=128, nif=64)
     enc.net[1] = torch.nn.BatchNorm2d(64)
@@ -126,6 +126,6 @@ def test_c_abi_argument_validation_without_a_gpu(built_lib):
     out = C.c_void_p()
     bad_first = layers([(3, 64, 5, 1, 2), (64, 128, 4, 2, 1), (128, 128, 4, 1, 0)])
     assert L.damc_pack_encoder(C.byref(out), 3, bad_first, 8, 8, 0.2, 1e-5, 1, None) == 2 and "layer 0" in err()
-    odd = layers([(1, 64, 3, 1, 1), (64, 128, 4, 2, 1), (128, 256, 4, 2, 1), (256, 128, 3, 1, 0)])   # 14 -> 7 -> 3: odd map
-    assert L.damc_pack_encoder(C.byref(out), 4, odd, 14, 14, 0.2, 1e-5, 1, None) == 2 and "odd" in err()
+    tiny = layers([(1, 64, 3, 1, 1), (64, 128, 4, 2, 1), (128, 256, 4, 2, 1), (256, 128, 1, 1, 0)])   # 2 -> 1 -> stride-2 conv of a 1 x 1 map
+    assert L.damc_pack_encoder(C.byref(out), 4, tiny, 2, 2, 0.2, 1e-5, 1, None) == 2 and "2 x 2" in err()
     assert L.damc_pack_encoder(C.byref(out), 3, bad_first, 8, 8, 0.2, 1e-5, 7, None) == 1 and "precision" in err()

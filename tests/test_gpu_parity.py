@@ -493,14 +493,36 @@ def test_encoder_families_match_torch(dataset, H, B, dev):
         assert e < ENC_TOL[prec], (dataset, prec, e)
 
 
-def test_encoder_rejects_odd_sized_maps(dev):
-    """The 28x28 MNIST encoder halves 7x7 maps: no parity-plane layout -> hard error, and damc_sample keeps it in torch."""
+@pytest.mark.parametrize("B", [1, 3, 130])
+def test_mnist_encoder_odd_maps_match_torch(B, dev):
+    """Encoder_mnist (reference diffusion_net.py:374-413): 28 -> 14 -> 7 -> 3 -> 1.  The 7x7 -> 3x3 stride-2 convolution runs on
+    zero-padded 4x4 parity planes; its InstanceNorm sees the 9 real outputs only.  Against the same module in torch fp32."""
     from damc_b200 import MCMC, diffusion_net as dn
-    enc = dn.Encoder("mnist", nc=1, nemb=128, nif=64).to(dev).eval()
-    x = torch.zeros(2, 1, 28, 28, device=dev)
-    assert not MCMC._encoder_on_library(enc, x)
-    with pytest.raises(RuntimeError):
-        MCMC.encoder_forward(enc, x, precision="bf16")
+    enc = dn.Encoder("mnist", nc=1, nemb=128, nif=64)
+    enc.load_state_dict(synth.module_state_like(enc, prefix="encm."))
+    enc = enc.to(dev).eval()
+    x = torch.tanh(synth.det_normal("xm", (B, 1, 28, 28))).to(dev)
+    assert MCMC._encoder_on_library(enc, x)
+    with torch.no_grad():
+        ref = enc(x)
+    for prec in ("fp32", "fp16", "bf16"):
+        out = MCMC.encoder_forward(enc, x, precision=prec)
+        e = relmax(out, ref)
+        print(f"mnist encoder B={B} [{prec}]: {e:.3e}")
+        assert e < ENC_TOL[prec], (prec, e)
+    # and the whole amortizer call of configs[4]: Q(x) with the encoder on the library
+    Q = dn._netQ_U(nc=1, nz=8, nxemb=128, ntemb=128, nif=64, diffusion_residual=True, n_interval=10, logsnr_min=-5.1,
+                   logsnr_max=9.8, var_type="large", with_noise=False, dataset="mnist")
+    Q.load_state_dict(synth.module_state_like(Q, prefix="Qm."))
+    Q = Q.to(dev).eval()
+    zi = synth.det_normal("zm", (B, 8)).to(dev)
+    # nz = 8 is below the tensor-core denoiser's granularity: fp32 persistent kernel, encoder on the library in fp16
+    z32 = MCMC.damc_sample(Q, x=x, z_init=zi, precision="fp32")     # torch's encoder + the same kernel
+    zl32 = MCMC.damc_sample(Q, x=x, z_init=zi, precision="fp32", encoder_precision="fp32")
+    z16 = MCMC.damc_sample(Q, x=x, z_init=zi, precision="fp32", encoder_precision="fp16")
+    e32, e16 = relmax(zl32, z32), relmax(z16, z32)
+    print(f"mnist Q(x) B={B}: library fp32 encoder {e32:.3e}, fp16 encoder {e16:.3e} (random-init sampler amplifies xemb errors ~100x)")
+    assert e32 < 5e-3 and torch.isfinite(z16).all() and e16 < 0.3
 
 
 def test_toy_amortizer_golden(dev):
