@@ -298,7 +298,8 @@ def run_ours(args):
                          "achieved_step": step_tflops, "frac_step": step_tflops / peak,
                          "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": pk["src"] + ("; tf32 peak = half of it" if args.precision == "tf32" else ""),
-                         "kernel": "convgemm_tc_kernel: generator implicit-GEMM launches (%d in the profiling pass of %d "
+                         "kernel": "convgemm_tc_kernel (+ last_fused_kernel, which contains the last layer's two GEMMs): generator "
+                                   "implicit-GEMM launches (%d in the profiling pass of %d "
                                    "steps, %.1f%% of that pass); frac / frac_gemm = algorithmic FLOPs / summed per-launch "
                                    "event time; frac_step = the same FLOPs / whole-step time of the hook-free timed region"
                                    % (gemm_n.value, prof_steps, 100.0 * gemm_ms.value / prof_ms)},

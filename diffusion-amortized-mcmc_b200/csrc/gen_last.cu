@@ -374,7 +374,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(bar_xfull, nx & 1u);
         ++nx;
         const int cy0 = max(0, L.need_lo + lr0);   // first image row held by the buffer
-        // (a 4-pixel batched form of this loop measured 3-8 % slower on the 3-channel shapes: more live registers, same chain)
+        // (a 4-pixel batched form of this loop measured 3-8 % slower on the 3-channel shapes, `#pragma unroll 2` 0-3 % slower)
         for (int p = lr0 * P.Wo + sid; p < lr1 * P.Wo; p += 128) {
           const int lrow = P.wo_shift >= 0 ? (p >> P.wo_shift) : p / P.Wo;
           const int ox = p - lrow * P.Wo, oy = L.need_lo + lrow;
