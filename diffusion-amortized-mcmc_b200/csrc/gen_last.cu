@@ -31,7 +31,7 @@
 
 namespace damc {
 
-constexpr int LF_THREADS = 512;           // warp 0 TMA, 1 scatter-MMA, 2 dgrad-MMA, 3 idle, 4-7 S group, 8-15 E group
+constexpr int LF_THREADS = 640;           // warp 0 TMA, 1 scatter-MMA, 2 dgrad-MMA, 3 idle, 4-7 S group A, 8-15 E group, 16-19 S group B
 constexpr int LF_TILE_BYTES = 128 * 128;  // 128 rows x one 128-byte swizzle row (64 16-bit elements)
 constexpr int LF_MAX_STAGES = 6;
 constexpr int LF_MAX_CHUNKS = 4;         // dgrad N chunks per tile (C <= 512)
@@ -52,6 +52,7 @@ struct LastParams {
   int wo_shift;                // log2(Wo) or -1
   int xr;                      // output rows of x held in smem at a time (>= n_need: the whole block in one chunk)
   int row_in_warp;             // 32 % Wi == 0: an image row never straddles two warps of the S group
+  int dual;                    // two pre-activation images: S group A accumulates the even tiles, B the odd ones (no races between them)
   int debug;                   // DAMC_LAST_DEBUG=1: CTA 0 prints where its warp groups spent their clocks
   const float* x;              // [B][nc][Ho][Wo]
   float* xhat;                 // same shape or null
@@ -138,7 +139,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(bar_a2full(a), 8); mbar_init(bar_a2empty(a), 1);
       mbar_init(bar_t3full(a), 1); mbar_init(bar_t3empty(a), 8);
     }
-    mbar_init(bar_gfull, 4);
+    mbar_init(bar_gfull, 8);
     mbar_init(bar_gempty, 8);
     mbar_init(bar_xfull, 1);
     fence_barrier_init();
@@ -149,6 +150,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
   for (int c = 0; c < NC; ++c) bias_r[c] = __ldg(P.bias + c);   // written by the pack kernels of an earlier, completed launch
   for (int i = threadIdx.x; i < P.out_floats; i += LF_THREADS) out_s[i] = __ldg(P.bias + i % NC);
+  if (P.dual) for (int i = threadIdx.x; i < P.out_floats; i += LF_THREADS) out_s[P.out_floats + i] = 0.f;
   for (int i = threadIdx.x; i < P.g_bytes / 4; i += LF_THREADS) reinterpret_cast<uint32_t*>(g_s)[i] = 0u;
   tc_fence_before();
   __syncthreads();
@@ -238,9 +240,17 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (P.debug && blockIdx.x == 0) printf("last_fused CTA0 dgrad-MMA: wait operand tile %u, wait accumulator %u\n", dbg0, dbg1);
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== S group: col2im accumulation (P1) and the likelihood gradient (P2) =====================
-    const int q = warp & 3, sid = threadIdx.x - 128;
+  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
+    // ===================== S groups A (warps 4-7) and B (16-19): col2im accumulation (P1), likelihood gradient (P2) =====
+    // P1: with two pre-activation images (P.dual) A takes the even tiles and TMEM accumulator 0, B the odd tiles and
+    // accumulator 1, each adding into its own image -- no ordering between the groups is needed, and the sum of the two images
+    // is formed in P2.  Without room for a second image A takes every tile and B only helps in P2.
+    // P2: both groups, 256 threads over the block's output pixels.
+    const bool is_s = warp < 8;
+    const int gidx = is_s ? 0 : 1;
+    float* const out_g = out_s + (P.dual ? gidx * P.out_floats : 0);
+    const int pass_bar = 1 + 2 * gidx;   // named barrier of this group's passes (1 | 3); 2 = both groups
+    const int q = warp & 3, sid = is_s ? threadIdx.x - 128 : threadIdx.x - 512 + 128;
     constexpr int NSC = K * K * NC;                 // live scatter columns
     constexpr int NLD = (NSC + 15) / 16 * 16;       // = Np_sc
     const uint32_t t_lane = tmem_y + ((uint32_t)(q * 32) << 16);
@@ -263,6 +273,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const LastBlock L = last_block<K, S>(P, blk);
       if (sid == 0) issue_x(L, 0);   // this block's x rows (first chunk) travel while the scatter GEMM runs
       for (int t = L.pt0; t < L.pt1; ++t, ++it) {
+        if (P.dual ? ((it & 1) != gidx) : !is_s) continue;
         const int as = it & 1;
         LF_T(dbg0, mbar_wait(bar_yfull(as), (uint32_t)(it >> 1) & 1u));
         tc_fence_after();
@@ -291,7 +302,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         auto tgt = [&](int kh, int kw, bool& ok) -> float* {
           const int oy = iy * S - P.pad + kh, ox = ix * S - P.pad + kw, lrow = oy - L.need_lo;
           ok = valid && oy >= 0 && oy < P.Ho && lrow >= 0 && lrow < L.n_need && ox >= 0 && ox < P.Wo;
-          return out_s + (lrow * P.Wo + ox) * NC;
+          return out_g + (lrow * P.Wo + ox) * NC;
         };
         if constexpr (S == 2) {
           // stride 2: the 2 x 2 slots {kh0, kh0+1} x {kw0, kw0+1} of ALL threads land on distinct pixels (distinct output
@@ -317,7 +328,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int c = 0; c < NC; ++c)
                     tp[j][c] = tv[j][c] + __uint_as_float(v[((kh0 + (j >> 1)) * K + kw0 + (j & 1)) * NC + c]);
                 }
-              if (P.row_in_warp && kw0 + 2 < K) __syncwarp(); else named_bar_sync(1, 128);
+              if (P.row_in_warp && kw0 + 2 < K) __syncwarp(); else named_bar_sync(pass_bar, 128);
             }
         } else {
           if (P.row_in_warp) {
@@ -339,7 +350,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < NC; ++c) tp[c] += tsum[c];
               }
-              named_bar_sync(1, 128);
+              named_bar_sync(pass_bar, 128);
             }
           } else {
 #pragma unroll
@@ -352,7 +363,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                   for (int c = 0; c < NC; ++c) tp[c] += __uint_as_float(v[(kh * K + kw) * NC + c]);
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(pass_bar, 128);
               }
           }
         }
@@ -362,20 +373,21 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // x arrives in smem by bulk copies issued at the START of the block (a dependent global load per pixel would expose a
       // loaded-DRAM round trip per iteration, ~3 k clocks each); blocks whose rows do not fit take it in several chunks.
       const int own0 = L.r0 * S, own1 = L.r1 * S;
+      named_bar_sync(2, 256);   // the pre-activation image is complete (S) -- the helpers may start (H)
       if (P.do_dgrad) LF_T(dbg2, mbar_wait(bar_gempty, ((uint32_t)nb & 1u) ^ 1u));   // the E group has gathered the previous block's gradient image
       float sq_acc = 0.f;
       const uint32_t tp2 = P.debug ? (uint32_t)clock() : 0u;
       for (int lr0 = 0; lr0 < L.n_need; lr0 += P.xr) {
         const int lr1 = min(L.n_need, lr0 + P.xr);
         if (lr0 > 0) {   // later chunk: every thread is done with the buffer, then one thread refills it
-          named_bar_sync(1, 128);
+          named_bar_sync(2, 256);
           if (sid == 0) issue_x(L, lr0);
         }
         mbar_wait(bar_xfull, nx & 1u);
         ++nx;
         const int cy0 = max(0, L.need_lo + lr0);   // first image row held by the buffer
         // (a 4-pixel batched form of this loop measured 3-8 % slower on the 3-channel shapes, `#pragma unroll 2` 0-3 % slower)
-        for (int p = lr0 * P.Wo + sid; p < lr1 * P.Wo; p += 128) {
+        for (int p = lr0 * P.Wo + sid; p < lr1 * P.Wo; p += 256) {
           const int lrow = P.wo_shift >= 0 ? (p >> P.wo_shift) : p / P.Wo;
           const int ox = p - lrow * P.Wo, oy = L.need_lo + lrow;
           float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -385,6 +397,10 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float h[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { h[c] = op[c]; op[c] = bias_r[c]; }
+            if (P.dual) {
+#pragma unroll
+              for (int c = 0; c < NC; ++c) { h[c] += op[P.out_floats + c]; op[P.out_floats + c] = 0.f; }
+            }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
               // tanh(h) = 1 - 2 / (e^{2h} + 1): absolute error ~1e-7 (x_hat enters only through x_hat - x and 1 - x_hat^2)
@@ -406,14 +422,14 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (P.do_dgrad) {
         if (lane == 0) mbar_arrive(bar_gfull);   // release: this warp's gradient pixels are visible to the E group
       } else if (P.sq_part != nullptr) {
-        // fixed-order reduction (lanes by shuffle tree, then warps 0..3): the per-chain squared error is bit-reproducible
+        // fixed-order reduction (lanes by shuffle tree, then the 8 warps in order): the per-chain squared error is bit-reproducible
         sq_acc = warp_sum(sq_acc);
         float* red = reinterpret_cast<float*>(gen_base + P.off_red);
-        if (lane == 0) red[q] = sq_acc;
-        named_bar_sync(1, 128);
-        if (sid == 0) P.sq_part[blk] = ((red[0] + red[1]) + red[2]) + red[3];
+        if (lane == 0) red[(is_s ? 0 : 4) + q] = sq_acc;
+        named_bar_sync(2, 256);
+        if (sid == 0) P.sq_part[blk] = (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
       }
-      named_bar_sync(1, 128);                  // every pre-activation is re-initialised before the next block accumulates
+      named_bar_sync(2, 256);                  // every pre-activation is re-initialised before the next block accumulates
     }
     if (P.debug && blockIdx.x == 0 && sid == 0)
       printf("last_fused CTA0 S group: wait scatter acc %u, col2im %u, wait gempty %u, P2 %u, blocks %d\n", dbg0, dbg1, dbg2, dbg3, nb);
@@ -421,11 +437,12 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       loss_acc = warp_sum(loss_acc);
       if (lane == 0 && loss_acc != 0.f) atomicAdd(P.loss, loss_acc);
     }
-  } else if (warp >= 8 && P.do_dgrad) {
+  } else if (warp >= 8 && warp < 16 && P.do_dgrad) {
     // ===================== E group: operand gather (P3a) and the masked dgrad epilogue (P3b) =====================
     const int q = warp & 3, half = (warp - 8) >> 2, eid = threadIdx.x - 256;
     int jb = 0, jc = 0, nb = 0;
-    uint32_t dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0, dbg4 = 0;
+    uint32_t dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0, dbg4 = 0, dbg5 = 0;
+    const uint32_t tstart_e = (uint32_t)clock();
     const int cw = P.chunkN >> 1;   // columns of a chunk handled by this warp
     const uint32_t t_lane = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * cw);
     uint32_t mnext[LF_MAX_CHUNKS][2];
@@ -494,6 +511,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           build(t + 1);
           if (t + 2 == L.t1) done_gather();
         }
+        const uint32_t tq = P.debug ? (uint32_t)clock() : 0u;
         const int r = q * 32 + lane;
         const bool valid = r < P.tile_rows;
         const int ry = r / P.Wi;
@@ -513,6 +531,7 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int ch = 0; ch < LF_MAX_CHUNKS; ++ch) { mcur[ch][0] = mnext[ch][0]; mcur[ch][1] = mnext[ch][1]; }
         if (t + 1 < L.t1) load_masks(L.b, t + 1, mnext);
+        if (P.debug) dbg5 += (uint32_t)clock() - tq;
 #pragma unroll
         for (int ch = 0; ch < LF_MAX_CHUNKS; ++ch) {
           if (ch < P.nchunks) {
@@ -556,8 +575,8 @@ last_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     if (P.debug && blockIdx.x == 0 && eid == 0)
-      printf("last_fused CTA0 E group: wait gfull %u, wait operand buffer %u, gather %u, wait dgrad acc %u, epilogue %u, chunks %d\n",
-             dbg0, dbg1, dbg2, dbg3, dbg4, jc);
+      printf("last_fused CTA0 E group: total %u, wait gfull %u, wait operand buffer %u, gather %u, tile setup + mask words %u, wait dgrad acc %u, epilogue %u, chunks %d\n",
+             (uint32_t)clock() - tstart_e, dbg0, dbg1, dbg2, dbg5, dbg3, dbg4, jc);
   }
   tc_fence_before();
   __syncthreads();
@@ -596,19 +615,22 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   if (P.Np_sc > 64 || P.Np_sc != (y.k * y.k * y.cout + 15) / 16 * 16) return false;
   const int halo_rows = same ? 2 : 1;
   const size_t wbytes = (size_t)P.kb_sc * P.Np_sc * 128 + (size_t)y.cin * 128;
-  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 16) + 96 + 1024;
+  const size_t fixed = 2 * LF_TILE_BYTES + wbytes + 8 * (2 * LF_MAX_STAGES + 16) + 112 + 1024;
   const size_t cap = 227 * 1024;
   auto need_rows = [&](int Rt) { return (Rt * P.Ht - 1) * y.stride - y.pad + y.k - 1 - (0 * y.stride - y.pad) + 1; };
   if (P.nchunks > LF_MAX_CHUNKS) return false;
   int best_rt = 0, best_stages = 0, best_xr = 0;
+  bool best_dual = false;
   for (int Rt = P.tpi; Rt >= 1 && !best_rt; --Rt) {
     if (Rt < P.tpi && Rt > 16) continue;
     const int nr = need_rows(Rt);
     for (int xchunks = 1; xchunks <= 3 && !best_rt; ++xchunks) {   // x rows staged per bulk copy: the whole block, or 1/2, 1/3 of it
       const int xr = ceil_div(nr, xchunks);
-      const size_t img = align_up((size_t)nr * y.Wout * y.cout * 4, 16) + align_up((size_t)nr * (y.Wout + 2) * 8, 16) +
-                         align_up((size_t)y.cout * xr * y.Wout * 4, 16);
+      const size_t outb = align_up((size_t)nr * y.Wout * y.cout * 4, 16);
+      size_t img = outb + align_up((size_t)nr * (y.Wout + 2) * 8, 16) + align_up((size_t)y.cout * xr * y.Wout * 4, 16);
       if (fixed + img + 4 * LF_TILE_BYTES > cap) continue;   // at least a 4-stage activation ring
+      best_dual = fixed + img + outb + 4 * LF_TILE_BYTES <= cap;   // room for the second pre-activation image
+      if (best_dual) img += outb;
       best_rt = Rt;
       best_xr = xr;
       best_stages = (int)std::min<size_t>(LF_MAX_STAGES, (cap - fixed - img) / LF_TILE_BYTES);
@@ -633,10 +655,11 @@ static bool last_plan(const GenPack* g, int B, LastPlan* out) {
   P.off_wsc = off; off += (uint32_t)(P.kb_sc * P.Np_sc * 128);   // multiples of 2 KB: every k-block slab stays 1024-aligned
   off = (uint32_t)align_up(off, 1024);
   P.off_wdg = off; off += (uint32_t)(y.cin * 128);
-  P.off_out = off; off += (uint32_t)align_up((size_t)P.out_floats * 4, 16);
+  P.dual = best_dual ? 1 : 0;
+  P.off_out = off; off += (uint32_t)align_up((size_t)P.out_floats * 4 * (P.dual ? 2 : 1), 16);
   P.off_g = off; off += (uint32_t)P.g_bytes;
   P.off_x = off; off += (uint32_t)align_up((size_t)y.cout * P.xr * y.Wout * 4, 16);
-  P.off_red = (uint32_t)align_up(off, 16); off = P.off_red + 16;
+  P.off_red = (uint32_t)align_up(off, 16); off = P.off_red + 32;
   P.off_bar = (uint32_t)align_up(off, 8);
   const size_t total = P.off_bar + 8 * (2 * LF_MAX_STAGES + 16) + 16 + 1024;
   if (total > cap) return false;
