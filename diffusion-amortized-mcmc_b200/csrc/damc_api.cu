@@ -72,6 +72,8 @@ int MlpPack::refill(cudaStream_t s, const int* dirty) {
   DAMC_TRY(launch_gated_copy(b3, src[5], 1, dirty, s));
   DAMC_TRY(launch_transpose(src[0], W1T, ndf, nz, s, dirty));   // from the caller's tensors: no dependence on the copies above
   DAMC_TRY(launch_transpose(src[2], W2T, ndf, ndf, s, dirty));
+  DAMC_TRY(ebm_tc_refill(this, DAMC_PREC_BF16, s, dirty));   // no-ops until the tensor-core step kernel has asked for them
+  DAMC_TRY(ebm_tc_refill(this, DAMC_PREC_FP16, s, dirty));
   return DAMC_OK;
 }
 
@@ -328,9 +330,15 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
       float* tr = trace ? trace + 4 * (size_t)i : nullptr;
       DAMC_TRY(generator_forward(g, ws, zz, B, xx, sigma, (i == K - 1) ? x_hat_out : nullptr, tr ? tr + 1 : nullptr, st));
       DAMC_TRY(generator_dgrad(g, ws, B, st));
-      DAMC_TRY(launch_ebm_step(m, zz, B, step_size, with_noise, noise ? noise + (size_t)i * B * g->nz : nullptr, seed,
-                               seed_ptr ? 0 : chain0, (seed_ptr ? 0 : step0) + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
-                               1.0f / generator_grad_scale(g, sigma), g->nz, st, seed_ptr));
+      const float* nz_i = noise ? noise + (size_t)i * B * g->nz : nullptr;
+      if (ebm_tc_usable(m, g->precision, tr))   // 16-bit modes, no trace: the EBM tail as four tcgen05 GEMMs per 128-chain tile
+        DAMC_TRY(launch_ebm_step_tc(m, g->precision, zz, B, step_size, with_noise, nz_i, seed, seed_ptr ? 0 : chain0,
+                                    (seed_ptr ? 0 : step0) + (uint64_t)i, ws.dz_part, S, g->nz_p, 1.0f / generator_grad_scale(g, sigma),
+                                    st, seed_ptr));
+      else
+        DAMC_TRY(launch_ebm_step(m, zz, B, step_size, with_noise, nz_i, seed,
+                                 seed_ptr ? 0 : chain0, (seed_ptr ? 0 : step0) + (uint64_t)i, tr, ws.dz_part, S, g->nz_p,
+                                 1.0f / generator_grad_scale(g, sigma), g->nz, st, seed_ptr));
     }
     return DAMC_OK;
   };

@@ -27,6 +27,9 @@ struct damc_handle {
 
 namespace damc {
 
+struct EbmTcPack;   // 16-bit, zero-padded copies of the EBM weights for the tensor-core step kernel (ebm_tc.cu)
+void ebm_tc_free(EbmTcPack* t);
+
 // ---- EBM MLP (weights kept in the reference's Linear layouts; the persistent kernel re-tiles them into smem) -------
 struct MlpPack : damc_handle {
   int nz = 0, ndf = 0;
@@ -35,7 +38,12 @@ struct MlpPack : damc_handle {
   float *W1T = nullptr, *W2T = nullptr;  // transposed copies [nz][ndf], [ndf][ndf] for the single-step kernel
   const float* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller's tensors (for damc_repack)
   float* slab = nullptr;
-  ~MlpPack() override { if (slab) cudaFree(slab); }
+  mutable EbmTcPack* tcp[2] = {nullptr, nullptr};   // [bf16, fp16]: built on first use by launch_ebm_step_tc, kept fresh by refill()
+  ~MlpPack() override {
+    if (slab) cudaFree(slab);
+    ebm_tc_free(tcp[0]);
+    ebm_tc_free(tcp[1]);
+  }
   int refill(cudaStream_t stream, const int* dirty) override;
   void sources(std::vector<HashSrc>& out) const override;
 };
@@ -56,6 +64,12 @@ int launch_ebm_step(const MlpPack* m, float* z, int B, float step, int with_nois
                     const unsigned long long* seed_ptr = nullptr /* non-null: {seed, chain0, step0} in device memory;
                                                                       chain0 / step_index arguments are then relative */);
 int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t stream, const int* dirty = nullptr);
+// the same step on the tensor cores (16-bit generator modes, no trace): one CTA per 128 chains, four tcgen05 GEMMs -- ebm_tc.cu
+bool ebm_tc_usable(const MlpPack* m, int precision, const float* trace);
+int ebm_tc_refill(const MlpPack* m, int precision, cudaStream_t s, const int* dirty);
+int launch_ebm_step_tc(const MlpPack* m, int precision, float* z, int B, float step, int with_noise, const float* noise,
+                       uint64_t seed, uint64_t chain0, uint64_t step_index, const float* gpart, int nsplit, int gstride,
+                       float gpart_scale, cudaStream_t stream, const unsigned long long* seed_ptr);
 
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
 // Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]

@@ -145,3 +145,75 @@ def test_posterior_score_matches_oracle(dataset, nz, ngf, nc, B, sigma, prec, to
     mse = MCMC.recon_mse(x.to(dev), z0.to(dev), G, precision=prec)
     mse_ref = ((xh - x.double()) ** 2).mean((1, 2, 3)).sum()
     assert abs(float(mse) - float(mse_ref)) < tol * float(mse_ref)
+
+
+# ---- EBM tail on the tensor cores (csrc/ebm_tc.cu) vs the CUDA-core step kernel ------------------------------------------------
+def _ebm_case(dataset, nz, ngf, nc, B, K, sigma, amp, dev):
+    from damc_b200 import diffusion_net as dn
+    layers = synth.gen_layers(dataset, nz, ngf, nc)
+    gsd, esd, z0, x, noise = synth.synth_problem(layers, nz, B, K, sigma, seed=3, gain=0.0)
+    esd = {k: (v * amp if k.endswith("weight") else v) for k, v in esd.items()}
+    G, E = dn._netG(dataset, nz, ngf, nc), dn._netE(nz)
+    G.load_state_dict(gsd)
+    E.load_state_dict(esd)
+    return G.to(dev), E.to(dev), layers, gsd, esd, z0, x, noise
+
+
+def _with_ebm_tc(flag, fn):
+    os.environ["DAMC_EBM_TC"] = flag
+    try:
+        return fn()
+    finally:
+        os.environ.pop("DAMC_EBM_TC", None)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("dataset,nz,ngf,nc,B,amp", [("mnist", 8, 128, 1, 200, 1.0), ("svhn", 100, 64, 3, 333, 1.0),
+                                                     ("cifar10", 128, 64, 3, 200, 4.0)])
+def test_ebm_gradient_on_tensor_cores(dataset, nz, ngf, nc, B, amp, prec, dev):
+    """dE/dz of ebm_tc_step_kernel (four tcgen05 GEMMs per 128-chain tile, fp16 operands, fp32 accumulation), recovered from ONE
+    noise-free posterior step with the likelihood switched off (sigma = 1e3), against the fp64 oracle (diffusion_net.py:212-223
+    through autograd in the reference).  dE/dz is discontinuous in the hidden pre-activations: a chain whose z rounding moves one of
+    the 2 ndf units across its LeakyReLU kink gets the exact gradient of a point 5e-4 away, which differs by a few per cent -- so
+    the bound is on the median chain and on the fraction of such chains (measured: median 4e-4, 4-6 % of the chains)."""
+    from damc_b200 import MCMC
+    G, E, layers, gsd, esd, z0, x, _ = _ebm_case(dataset, nz, ngf, nc, B, 1, 0.1, amp, dev)
+    gref = O.ebm_grad(synth.ebm_list_from_state(esd, torch.float64), z0.double())[1]
+    s = 0.1
+
+    def grad():
+        out = MCMC.sample_langevin_post_z_with_prior(z0.to(dev).clone().requires_grad_(True), x.to(dev), G, E, 1, 1e3, False, s,
+                                                     precision=prec).cpu().double()
+        return (z0.double() - out) / (0.5 * s * s) - z0.double()
+
+    g_tc, g_cc = _with_ebm_tc("1", grad), _with_ebm_tc("0", grad)
+    per_tc = ((g_tc - gref).abs().amax(1) / gref.abs().amax(1)).numpy()
+    per_cc = ((g_cc - gref).abs().amax(1) / gref.abs().amax(1)).numpy()
+    print(f"{dataset} amp={amp} [{prec}]: dE/dz per-chain err  tensor cores median {np.median(per_tc):.3e} max {per_tc.max():.3e} "
+          f"frac>1e-2 {(per_tc > 1e-2).mean():.2f}   CUDA cores median {np.median(per_cc):.3e} max {per_cc.max():.3e}")
+    assert per_cc.max() < 1e-3
+    assert not torch.equal(g_tc, g_cc)                          # two different code paths really ran
+    assert np.median(per_tc) < 2e-3 and (per_tc > 1e-2).mean() < 0.2 and per_tc.max() < 0.6
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 2e-3), ("fp16", 1e-3)])
+def test_posterior_with_tensor_core_ebm_tail_matches_cuda_core_tail(prec, tol, dev):
+    """K steps at the benchmark's regime (default-init weights): the same run with the EBM tail on the tensor cores and on the
+    CUDA cores, injected noise and Philox noise (same draw in both kernels), ragged batch (two tiles, the second partly empty)."""
+    from damc_b200 import MCMC
+    K, B, sigma = 4, 150, 0.1
+    G, E, layers, gsd, esd, z0, x, noise = _ebm_case("cifar10", 128, 64, 3, B, K, sigma, 1.0, dev)
+
+    def run(**kw):
+        return MCMC.sample_langevin_post_z_with_prior(z0.to(dev).clone().requires_grad_(True), x.to(dev), G, E, K, sigma, True, 0.1,
+                                                      precision=prec, **kw).cpu().double()
+
+    for name, kw in (("injected", dict(noise=noise.to(dev))), ("philox", dict(seed=11, chain0=5, step0=2))):
+        a, b = _with_ebm_tc("1", lambda: run(**kw)), _with_ebm_tc("0", lambda: run(**kw))
+        e = float((a - b).abs().max() / b.abs().max())
+        print(f"[{prec}] {name}: posterior z with tensor-core vs CUDA-core EBM tail {e:.3e}")
+        assert 0.0 < e < tol, (name, e)
+    gen64, ebm64 = synth.gen_list_from_state(gsd, layers, torch.float64), synth.ebm_list_from_state(esd, torch.float64)
+    ref = O.langevin_posterior(z0.double(), x.double(), gen64, ebm64, K, sigma, True, 0.1, noise.double())
+    a = _with_ebm_tc("1", lambda: run(noise=noise.to(dev)))
+    assert float((a - ref).abs().max() / ref.abs().max()) < (2e-2 if prec == "bf16" else 4e-3)
