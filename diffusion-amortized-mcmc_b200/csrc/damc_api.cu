@@ -347,7 +347,8 @@ int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, floa
   static const bool use_graph = []{ const char* e = getenv("DAMC_GRAPH"); return !(e && e[0] == '0'); }();
   const bool graphable = use_graph && g->use_tc && !profiling() && noise == nullptr && trace == nullptr && K > 1;
   if (!graphable) return issue(z, x, nullptr, s);
-  const GenPack::GraphKey key = {B, K, with_noise, x_hat_out != nullptr ? 1 : 0, step_size, sigma, ws.base, m ? m->uid : 0ull};
+  // (bit 1 of the noise field: which form of the EBM tail the sequence launches -- DAMC_EBM_TC may change between calls)
+  const GenPack::GraphKey key = {B, K, with_noise | (ebm_tc_usable(m, g->precision, nullptr) ? 2 : 0), x_hat_out != nullptr ? 1 : 0, step_size, sigma, ws.base, m ? m->uid : 0ull};
   auto same = [&](const GenPack::GraphKey& k0) {
     return k0.B == key.B && k0.K == key.K && k0.with_noise == key.with_noise && k0.want_xhat == key.want_xhat &&
            k0.step == key.step && k0.sigma == key.sigma && k0.ws_base == key.ws_base && k0.ebm == key.ebm;
