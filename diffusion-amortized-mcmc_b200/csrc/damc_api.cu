@@ -276,6 +276,27 @@ int damc_generator_forward(const damc_handle* gen, const float* z, float* x_hat,
   return generator_forward(g, ws, z, B, nullptr, 1.0f, x_hat, nullptr, (cudaStream_t)stream);
 }
 
+// D[m][n] = sum_k A[m][k] W[n][k] (+ bias[n]) on the tcgen05 engine, kind::tf32 (fp32 tensors as they are: the MMA reads the top
+// 19 bits of each operand).  The plain-GEMM plan of the generator's first layer: a 1 x 1 pixel grid, M "chains", one tap.
+int damc_gemm_tf32(const float* A, const float* W, const float* bias, float* D, int M, int N, int K, int ldd, void* stream) {
+  if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) DAMC_FAIL(DAMC_ERR_INVALID, "damc_gemm_tf32: bad arguments");
+  if (K % 32 || N % 16 || ldd < N || ldd % 4) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "damc_gemm_tf32: K %% 32, N %% 16, ldd %% 4 == 0 required (M=%d N=%d K=%d ldd=%d)", M, N, K, ldd);
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)D) & 15) DAMC_FAIL(DAMC_ERR_INVALID, "damc_gemm_tf32: pointers must be 16-byte aligned");
+  DAMC_TRY(check_sm100());
+  GemmPlan p{};
+  p.A = A; p.B = M; p.Hm = 1; p.Wm = 1; p.Cs = K;
+  p.ntaps = 1; p.taps[0] = Tap{0, 0, 0, 0};
+  p.N = p.Np = N; p.ksplit = 1;
+  p.Wtc = W;
+  p.epi.kind = bias ? EPI_STORE_F32_BIAS : EPI_STORE_F32;
+  p.epi.bias = bias;
+  p.epi.out = D;
+  p.epi.nz_out = ldd;
+  const int r = launch_gemm_tc(p, DAMC_PREC_TF32, (cudaStream_t)stream);
+  count_launch();
+  return r;
+}
+
 int damc_posterior_score(const damc_handle* gen, const damc_handle* ebm, const float* z, const float* x, int B, float* score,
                          float* sqerr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!gen || gen->kind != H_GEN) DAMC_FAIL(DAMC_ERR_INVALID, "damc_posterior_score: not a generator handle");

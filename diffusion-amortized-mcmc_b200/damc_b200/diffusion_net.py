@@ -211,9 +211,12 @@ class _netQ_U(nn.Module):
         from . import MCMC  # late import: MCMC needs the CUDA library
         return MCMC.damc_sample(self, x=x, b=b, device=device, cond_w=cond_w, noise=noise, precision=precision)
 
-    def calculate_loss(self, x=None, z=None, mask=None):
+    def calculate_loss(self, x=None, z=None, mask=None, engine="torch"):
         """Denoising loss 0.5*|eps - eps_hat|^2 per sample at a random noise level (reference diffusion_net.py:624-646).
-        Training-side code: ordinary PyTorch autograd (outside the CUDA hot path)."""
+        engine="torch": ordinary PyTorch autograd, as the reference.  engine="library": the 35 Linear layers of the seven
+        ConcatSquashLinearSkipCtx blocks of Q.p run forward AND backward as tcgen05 TF32 GEMMs of libdamc_b200
+        (damc_b200/denoiser_train.py); encoder, prior_emb, time_mlp and the loss stay autograd.  Same random draws either way.
+        engine="library_graphed": the same, with the core's forward and backward replayed from CUDA graphs."""
         assert z is not None
         n = len(z)
         if x is not None:
@@ -228,7 +231,13 @@ class _netQ_U(nn.Module):
         lam = logsnr.reshape(n, 1)
         eps = torch.randn_like(z)
         zt = z * torch.sqrt(torch.sigmoid(lam)) + torch.sqrt(torch.sigmoid(-lam)) * eps
-        eps_pred = self.p(z=zt, logsnr=logsnr, xemb=xemb)
+        if engine in ("library", "library_graphed"):
+            from . import denoiser_train
+            eps_pred = denoiser_train.eps_network(self.p, zt, logsnr, xemb, graphed=engine == "library_graphed")
+        elif engine == "torch":
+            eps_pred = self.p(z=zt, logsnr=logsnr, xemb=xemb)
+        else:
+            raise ValueError("engine must be 'torch', 'library' or 'library_graphed'")
         return 0.5 * torch.sum((eps - eps_pred) ** 2, dim=1)
 
 

@@ -29,6 +29,7 @@ class TrainConfig:  # defaults = train_gen_recon.py:383-402
     q_updates: int = 6
     max_norm: float = 100.0
     precision: str = "tf32"   # what the reference's cuDNN convolutions compute in by default on a GPU
+    q_loss_engine: str = "torch"   # "library" | "library_graphed": the Linear layers of Q.p in Q.calculate_loss on the tcgen05 TF32 GEMMs
 
 
 def _step(loss, params, opt, cfg, group):
@@ -75,7 +76,7 @@ def training_iteration(x, G, E, Q, Q_dummy, G_opt, E_opt, Q_opt, cfg=TrainConfig
     q_params, g_params, e_params = list(Q.parameters()), list(G.parameters()), list(E.parameters())
     Q.train()
     for _ in range(cfg.q_updates):
-        q_loss = Q.calculate_loss(x=x, z=zk_pos, mask=z_mask).mean()
+        q_loss = Q.calculate_loss(x=x, z=zk_pos, mask=z_mask, engine=cfg.q_loss_engine).mean()
         _step(q_loss, q_params, Q_opt, cfg, group)
     G.train()
     g_loss = torch.sum((G(zk_pos) - x) ** 2, dim=[1, 2, 3]).mean()

@@ -187,6 +187,12 @@ int damc_fused_clip_adam(float* params, const float* grads, float* exp_avg, floa
                          float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, float max_norm,
                          float grad_scale, float* scratch, void* stream);
 
+/* ---- plain GEMM on the tcgen05 engine, TF32 operands / fp32 accumulate: D[m][n] = sum_k A[m][k] W[n][k] (+ bias[n]) ------------
+ * A [M][K] and W [N][K] row-major fp32 (W is nn.Linear's weight layout), D [M][ldd].  K % 32 == 0, N % 16 == 0.
+ * Used by damc_b200.denoiser_train for the Linear layers of Q.p in Q.calculate_loss (reference diffusion_net.py:417-445,
+ * :624-646): forward X W^T, input-gradient dY W, weight-gradient dY^T X are all this one form on (transposed) copies.     */
+int damc_gemm_tf32(const float* A, const float* W, const float* bias, float* D, int M, int N, int K, int ldd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,9 +34,9 @@ def main():
     Q0 = dn._netQ_U(nc=3, nz=128, nxemb=1024, ntemb=128, nif=64, diffusion_residual=True, n_interval=100, logsnr_min=-5.1,
                     logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10").to(dev)
     x = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
-    cfg = train.TrainConfig(precision=os.environ.get("PREC", "bf16"))
+    cfg = train.TrainConfig(precision=os.environ.get("PREC", "bf16"), q_loss_engine=os.environ.get("Q_ENGINE", "torch"))
     MCMC.set_default_denoiser_precision("fp16")
-    out = {"world": world, "chains_per_gpu": B, "precision": cfg.precision}
+    out = {"world": world, "chains_per_gpu": B, "precision": cfg.precision, "q_loss_engine": cfg.q_loss_engine}
 
     def run(kind):
         G, E, Q = copy.deepcopy(G0), copy.deepcopy(E0), copy.deepcopy(Q0)
