@@ -83,9 +83,28 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
   }
 }
 
+// fp32 -> nearest TF32 value (ties away from zero), kept in fp32 containers: the tcgen05 kind::tf32 MMA reads the top 19 bits of
+// its operands, i.e. TRUNCATES; rounding the operands first halves the perturbation (what cuBLAS' TF32 path does)
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+    dst[i] = __uint_as_float(r);
+  }
+}
+
 }  // namespace damc
 
 using namespace damc;
+
+extern "C" int damc_round_tf32(const float* src, float* dst, size_t n, void* stream) {
+  if (!src || !dst) DAMC_FAIL(DAMC_ERR_INVALID, "damc_round_tf32: null argument");
+  if (n == 0) return DAMC_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  round_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  DAMC_CUDA(cudaGetLastError());
+  return DAMC_OK;
+}
 
 extern "C" int damc_fused_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n_total,
                                     int nranges, const unsigned long long* range_begin, const unsigned long long* range_count,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "damc_generator_forward": (_I, [_P, _P, _P, _I, _P, _SZ, _P]),
     "damc_posterior_score": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _SZ, _P]),
     "damc_fused_clip_adam": (_I, [_P, _P, _P, _P, _SZ, _I, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _F, _P, _P]),
+    "damc_round_tf32": (_I, [_P, _P, _SZ, _P]),
     "damc_gemm_tf32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "damc_prior_langevin": (_I, [_P, _P, _I, _I, _F, _I, _P, _U64, _U64, _U64, _P, _P]),
     "damc_posterior_langevin": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _U64, _U64, _U64, _P, _P, _P, _SZ, _P]),

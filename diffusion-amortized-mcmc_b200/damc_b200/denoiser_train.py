@@ -26,10 +26,21 @@ _LAYERS = (("in_layers", 0), ("in_layers", 1), ("in_layers", 2), ("mid_layers", 
            ("out_layers", 2))
 
 
+def _tf32(t):
+    """Contiguous copy of t rounded to the nearest TF32 values (damc_round_tf32): the MMA would otherwise truncate the operand."""
+    src = t.contiguous()
+    dst = torch.empty_like(src)
+    with torch.cuda.device(t.device):
+        check(lib().damc_round_tf32(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), src.numel(),
+                                    C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)), "damc_round_tf32")
+    return dst
+
+
 def gemm(A, W, bias=None, out=None):
-    """out[m, n] = sum_k A[m, k] W[n, k] (+ bias[n]) through damc_gemm_tf32.  A [M, K], W [N, K] contiguous fp32 CUDA tensors."""
+    """out[m, n] = sum_k A[m, k] W[n, k] (+ bias[n]) through damc_gemm_tf32.  A [M, K], W [N, K] fp32 CUDA tensors (rounded to
+    TF32 copies here)."""
     assert A.is_cuda and A.dtype == torch.float32 and W.dtype == torch.float32 and A.dim() == 2 and W.dim() == 2
-    A, W = A.contiguous(), W.contiguous()
+    A, W = _tf32(A), _tf32(W)
     M, K = A.shape
     N = W.shape[0]
     if W.shape[1] != K:

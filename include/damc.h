@@ -192,6 +192,9 @@ int damc_fused_clip_adam(float* params, const float* grads, float* exp_avg, floa
  * Used by damc_b200.denoiser_train for the Linear layers of Q.p in Q.calculate_loss (reference diffusion_net.py:417-445,
  * :624-646): forward X W^T, input-gradient dY W, weight-gradient dY^T X are all this one form on (transposed) copies.     */
 int damc_gemm_tf32(const float* A, const float* W, const float* bias, float* D, int M, int N, int K, int ldd, void* stream);
+/* dst[i] = src[i] rounded to the nearest TF32 value (cvt.rna), fp32 container; dst may equal src.  The MMA above truncates its
+ * operands; rounding them first (as cuBLAS' TF32 path does) halves the perturbation of damc_gemm_tf32.                          */
+int damc_round_tf32(const float* src, float* dst, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

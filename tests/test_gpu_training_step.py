@@ -128,7 +128,7 @@ def test_q_loss_on_library_gemms_matches_autograd(B, dev):
             assert torch.equal(g3[n], g1[n]), n                       # the core's own outputs: bit for bit
         else:                                                         # downstream of the core through cuDNN / cuBLAS backward kernels
             assert float((g3[n] - g1[n]).abs().max()) <= 1e-5 * gmax, n
-    assert set(g0) == set(g1) == set(ge) and launches == 46           # 16 forward + 30 backward GEMM launches on the library
+    assert set(g0) == set(g1) == set(ge) and launches == 46           # 16 forward + 30 backward GEMM launches on the library (rounding passes not counted)
     norm = lambda g: sum(float((v ** 2).sum()) for v in g.values()) ** 0.5
     diff = lambda a, b: sum(float(((a[n] - b[n]) ** 2).sum()) for n in a) ** 0.5
     e_exact, e_lib, e_tf = diff(ge, g0) / norm(g0), diff(g1, g0) / norm(g0), diff(gt, g0) / norm(g0)
@@ -136,9 +136,9 @@ def test_q_loss_on_library_gemms_matches_autograd(B, dev):
           f"stand-in {e_exact:.2e}, library {e_lib:.3e}, torch TF32 {e_tf:.3e}")
     assert abs(le - l0) <= 1e-5 * abs(l0) and e_exact < 1e-5
     assert abs(l1 - l0) <= 2e-3 * abs(l0), (l0, l1)
-    assert e_lib < max(3 * e_tf, 2e-3), (e_lib, e_tf)
+    assert e_lib < max(1.5 * e_tf, 2e-3), (e_lib, e_tf)
     big = [n for n in g0 if float(g0[n].abs().max()) > 1e-3 * max(float(v.abs().max()) for v in g0.values())]
     for n in big:
         a = float(((g1[n] - g0[n]) ** 2).sum()) ** 0.5 / (float((g0[n] ** 2).sum()) ** 0.5)
         b = float(((gt[n] - g0[n]) ** 2).sum()) ** 0.5 / (float((g0[n] ** 2).sum()) ** 0.5)
-        assert a < max(6 * b, 0.1), (n, a, b)   # (operands are truncated, not rounded, to TF32: ~2x torch's perturbation)
+        assert a < max(3 * b, 0.08), (n, a, b)
