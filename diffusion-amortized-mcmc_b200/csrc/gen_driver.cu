@@ -17,7 +17,9 @@ static int dz_splits_for(const GenPack* g, int B) {
   const int mt = ceil_div(B, 128);
   const GenLayer& f = g->layers[0];
   const int kb = f.k * f.k * f.cout / 64;
-  // (128 splits at 128 chains were tried: the GEMM drops 46 -> 38 us but the update kernel's partial-sum reads grow by as much)
+  // (128 splits at 128 chains were tried twice: round 1 the GEMM dropped 46 -> 38 us but the update kernel's partial-sum reads grew
+  //  by as much; round 2, with the partials pre-summed by dz_reduce_kernel, the step time did not move (17.2 ms either way) -- and a
+  //  cap that binds at every tested batch size is what keeps the split count, hence the summation order, shard-invariant)
   int s = std::max(1, std::min(std::min(32, kb), 296 / mt));
   while (s > 1 && (long long)ceil_div(kb, s) * (s - 1) >= kb) --s;
   return s;

@@ -142,3 +142,23 @@ def test_q_loss_on_library_gemms_matches_autograd(B, dev):
         a = float(((g1[n] - g0[n]) ** 2).sum()) ** 0.5 / (float((g0[n] ** 2).sum()) ** 0.5)
         b = float(((gt[n] - g0[n]) ** 2).sum()) ** 0.5 / (float((g0[n] ** 2).sum()) ** 0.5)
         assert a < max(3 * b, 0.08), (n, a, b)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 1408, 1152), (12, 256, 512), (512, 256, 32), (300, 272, 96), (1408, 1152, 128)])
+def test_gemm_tf32_abi_matches_matmul(M, N, K, dev):
+    """damc_gemm_tf32 (the tcgen05 engine's plain-GEMM plan, kind::tf32) through the C ABI: D = A W^T (+ bias), ragged M, N that is
+    not a multiple of the 256-column tile, one 32-wide k-block, a strided output (column slice of a wider tensor)."""
+    from damc_b200 import denoiser_train as dt
+    torch.manual_seed(M + N + K)
+    A, W, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.randn(N, device=dev)
+    ref = A.double() @ W.double().t()
+    for bias in (None, b):
+        out = dt.gemm(A, W, bias)
+        r = ref + (bias.double() if bias is not None else 0)
+        assert float((out.double() - r).abs().max() / r.abs().max()) < 1e-3       # TF32 operands (rounded), fp32 accumulation
+    wide = torch.full((M, N + 64), 7.0, device=dev)
+    dt.gemm(A, W, None, out=wide[:, 32:32 + N])
+    assert float((wide[:, 32:32 + N].double() - ref).abs().max() / ref.abs().max()) < 1e-3
+    assert bool((wide[:, :32] == 7.0).all()) and bool((wide[:, 32 + N:] == 7.0).all())   # nothing outside the slice is touched
+    t = dt._tf32(A)
+    assert float((t - A).abs().max() / A.abs().max()) < 2.0 ** -11 and bool(((t.view(torch.int32) & 0x1FFF) == 0).all())
