@@ -325,6 +325,17 @@ int damc_prior_langevin(const damc_handle* ebm, float* z, int B, int K, float st
                              step0, trace, 2, nullptr, 0, 0, 0, s);
 }
 
+int damc_prior_langevin_tc(const damc_handle* ebm, float* z, int B, int K, float step_size, int with_noise, const float* noise,
+                           uint64_t seed, uint64_t chain0, uint64_t step0, void* stream) {
+  if (!ebm || ebm->kind != H_MLP) DAMC_FAIL(DAMC_ERR_INVALID, "damc_prior_langevin_tc: not an EBM handle");
+  if (!z || B <= 0 || K < 0) DAMC_FAIL(DAMC_ERR_INVALID, "damc_prior_langevin_tc: bad arguments");
+  const MlpPack* m = static_cast<const MlpPack*>(ebm);
+  if (!ebm_tc_usable(m, DAMC_PREC_FP16, nullptr))
+    DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "damc_prior_langevin_tc: needs nz %% 4 == 0, nz <= 128, ndf <= 256 (nz=%d ndf=%d) and DAMC_EBM_TC != 0", m->nz, m->ndf);
+  return launch_ebm_step_tc(m, DAMC_PREC_FP16, z, B, step_size, with_noise, noise, seed, chain0, step0, nullptr, 0, 0, 1.0f,
+                            (cudaStream_t)stream, nullptr, K);
+}
+
 int damc_posterior_langevin(const damc_handle* gen, const damc_handle* ebm, float* z, const float* x, int B, int K,
                             float step_size, float sigma, int with_noise, const float* noise, uint64_t seed,
                             uint64_t chain0, uint64_t step0, float* trace, float* x_hat_out, void* workspace,

@@ -69,7 +69,7 @@ bool ebm_tc_usable(const MlpPack* m, int precision, const float* trace);
 int ebm_tc_refill(const MlpPack* m, int precision, cudaStream_t s, const int* dirty);
 int launch_ebm_step_tc(const MlpPack* m, int precision, float* z, int B, float step, int with_noise, const float* noise,
                        uint64_t seed, uint64_t chain0, uint64_t step_index, const float* gpart, int nsplit, int gstride,
-                       float gpart_scale, cudaStream_t stream, const unsigned long long* seed_ptr);
+                       float gpart_scale, cudaStream_t stream, const unsigned long long* seed_ptr, int K = 1);
 
 // ---- generator as a chain of shifted-window GEMMs --------------------------------------------------------------
 // Every layer's forward and input-gradient is   D[m,n] = sum_t sum_c A_t[m,c] * W_t[c,n]

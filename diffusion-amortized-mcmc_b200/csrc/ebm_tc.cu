@@ -101,6 +101,8 @@ struct EbmTcArgs {
   const float* vec;   // b1 | b2 | w3, 256 floats each
   int op_fp16;
   uint32_t idesc_h, idesc_z;
+  int K;                      // Langevin steps in this launch (posterior tail: 1; prior sampler: all K, weights re-streamed per step)
+  long long noise_stride;     // elements between the injected-noise slabs of consecutive steps
 };
 
 __global__ void __launch_bounds__(ET_THREADS, 1)
@@ -144,6 +146,7 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const CUtensorMap* tms[4] = {&tmW1, &tmW2, &tmW2T, &tmW1T};
+      for (int it = 0; it < a.K; ++it)
       for (int g = 0; g < 4; ++g)
         for (int kb = 0; kb < nkb[g]; ++kb) {
           mbar_wait(bar_wempty(stage), phase ^ 1u);
@@ -156,8 +159,9 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int it = 0; it < a.K; ++it)
       for (int g = 0; g < 4; ++g) {
-        mbar_wait(bar_ready, (uint32_t)g & 1u);   // the operand tile of GEMM g is in shared memory
+        mbar_wait(bar_ready, (uint32_t)g & 1u);   // the operand tile of GEMM g is in shared memory (4 phases per step: same parities)
         tc_fence_after();
         const uint32_t abuf = (g & 1) ? bufA : bufB;
         for (int kb = 0; kb < nkb[g]; ++kb) {
@@ -194,6 +198,7 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     // ---- operand of GEMM 0: the z tile.  A warp takes 16 rows; a row is one coalesced 512-byte read (lane = 4 columns); four
     // rows' loads are in flight before the first is converted ----
     const int c4 = lane * 4;
+    for (int it = 0; it < a.K; ++it) {
 #pragma unroll 1
     for (int r0 = 0; r0 < 16; r0 += 4) {
       float4 zq[4];
@@ -280,7 +285,8 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     const float half_s2 = 0.5f * a.step * a.step;
     const unsigned long long seed = a.seed_ptr ? a.seed_ptr[0] : a.seed;
     const unsigned long long chain_base = (a.seed_ptr ? a.seed_ptr[1] : a.chain0) + (unsigned long long)blockIdx.x * 128ull;
-    const unsigned long long stp = (a.seed_ptr ? a.seed_ptr[2] : 0ull) + a.step_index;
+    const unsigned long long stp = (a.seed_ptr ? a.seed_ptr[2] : 0ull) + a.step_index + (unsigned long long)it;
+    const float* noise_it = a.noise ? a.noise + (long long)it * a.noise_stride : nullptr;
     const bool live = c4 < a.nz;                     // nz % 4 == 0: a quad is either live or padding
 #pragma unroll 1
     for (int r0 = 0; r0 < 16; r0 += 4) {
@@ -293,7 +299,7 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         zq[u] = okr ? *reinterpret_cast<const float4*>(a.z + bb * a.nz + c4) : zero;
         gq[u] = (okr && a.gpart != nullptr) ? *reinterpret_cast<const float4*>(a.gpart + (size_t)bb * a.gstride + c4) : zero;   // split 0 = the reduced sum
-        nq[u] = (okr && a.with_noise && a.noise) ? *reinterpret_cast<const float4*>(a.noise + bb * a.nz + c4) : zero;
+        nq[u] = (okr && a.with_noise && noise_it) ? *reinterpret_cast<const float4*>(noise_it + bb * a.nz + c4) : zero;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -302,7 +308,7 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         if (!(live && bb < a.B)) continue;
         const float4 ge = gbuf[R * qpr + (lane ^ (R & (qpr - 1)))];
         float nrm[4] = {nq[u].x, nq[u].y, nq[u].z, nq[u].w};
-        if (a.with_noise && !a.noise) philox_normal4(seed, chain_base + (unsigned long long)R, stp, (uint32_t)lane, nrm);
+        if (a.with_noise && !noise_it) philox_normal4(seed, chain_base + (unsigned long long)R, stp, (uint32_t)lane, nrm);
         const float zv[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w}, gG[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
         const float gE[4] = {ge.x, ge.y, ge.z, ge.w};
         float zn[4];
@@ -314,6 +320,9 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         *reinterpret_cast<float4*>(a.z + bb * a.nz + c4) = make_float4(zn[0], zn[1], zn[2], zn[3]);
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp is done with the fp32 tile in bufB before the next step's z tile lands there
+    }   // step loop
+
   }
   __syncthreads();
   if (warp == 1) {
@@ -382,8 +391,9 @@ static int ebm_tc_ensure(const MlpPack* m, int precision, cudaStream_t s) {
 
 int launch_ebm_step_tc(const MlpPack* m, int precision, float* z, int B, float step, int with_noise, const float* noise,
                        uint64_t seed, uint64_t chain0, uint64_t step_index, const float* gpart, int nsplit, int gstride,
-                       float gpart_scale, cudaStream_t stream, const unsigned long long* seed_ptr) {
+                       float gpart_scale, cudaStream_t stream, const unsigned long long* seed_ptr, int K) {
   (void)precision;
+  if (K < 1) return DAMC_OK;
   DAMC_TRY(ebm_tc_ensure(m, ET_PREC, stream));
   const EbmTcPack* t = m->tcp[tc_slot(ET_PREC)];
   EbmTcArgs a{};
@@ -391,6 +401,8 @@ int launch_ebm_step_tc(const MlpPack* m, int precision, float* z, int B, float s
   a.seed = seed; a.chain0 = chain0; a.step_index = step_index; a.seed_ptr = seed_ptr;
   a.gpart = gpart; a.nsplit = nsplit; a.gstride = gstride; a.gpart_scale = gpart_scale;
   a.vec = t->vec;
+  a.K = K;
+  a.noise_stride = (long long)B * m->nz;
   a.op_fp16 = ET_PREC == DAMC_PREC_FP16 ? 1 : 0;
   const uint32_t opfmt = a.op_fp16 ? 0u : 1u;
   a.idesc_h = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(ET_H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -219,9 +219,12 @@ def _chain_tensor(z, what="z"):
 # samplers
 # ----------------------------------------------------------------------------------------------------------------------
 def sample_langevin_prior_z(z, netE, e_l_steps, e_l_step_size, e_l_with_noise, verbose=False, *, noise=None,
-                            seed=None, chain0=0, step0=0):
+                            seed=None, chain0=0, step0=0, precision=None):
     """K-step Langevin on E(z) + |z|^2/2, all steps in one persistent kernel.  Updates ``z.data`` in place and returns
-    ``z.detach()`` like the reference (MCMC.py:36,46).  noise: optional injected normals [K,B,nz]."""
+    ``z.detach()`` like the reference (MCMC.py:36,46).  noise: optional injected normals [K,B,nz].
+    precision: None / 'fp32' = the fp32 kernel with the MLP resident in shared memory (parity mode, best up to a few thousand
+    chains); 'fp16' = the MLP's mat-mat products on the tensor cores, one CTA per 128 chains (damc_prior_langevin_tc: the
+    large-batch form, 16-bit accuracy of dE/dz, no verbose trace)."""
     zd = _chain_tensor(z)
     B, nz = zd.shape
     h = pack_ebm(netE)
@@ -229,6 +232,18 @@ def sample_langevin_prior_z(z, netE, e_l_steps, e_l_step_size, e_l_with_noise, v
     K = int(e_l_steps)
     keep, nptr = _noise_ptr(noise, (K, B, nz), zd.device)
     trace = torch.empty(K, 2, dtype=torch.float32, device=zd.device) if verbose and K > 0 else None
+    if precision not in (None, "fp32", "fp16"):
+        raise ValueError("prior sampler precision must be None / 'fp32' or 'fp16'")
+    if precision == "fp16":
+        if verbose:
+            raise RuntimeError("precision='fp16' (tensor-core prior sampler) has no verbose trace; use the fp32 kernel")
+        with torch.cuda.device(zd.device):
+            check(lib().damc_prior_langevin_tc(h.ptr, C.c_void_p(zd.data_ptr()), B, K, float(e_l_step_size),
+                                               int(bool(e_l_with_noise)), nptr,
+                                               _draw_seed() if (seed is None and noise is None and e_l_with_noise) else int(seed or 0),
+                                               int(chain0), int(step0), _stream(zd.device)), "damc_prior_langevin_tc")
+        set_requires_grad(netE, requires_grad=True)
+        return z.detach()
     with torch.cuda.device(zd.device):
         check(lib().damc_prior_langevin(h.ptr, C.c_void_p(zd.data_ptr()), B, K, float(e_l_step_size),
                                         int(bool(e_l_with_noise)), nptr,

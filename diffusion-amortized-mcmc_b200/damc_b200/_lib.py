@@ -46,6 +46,7 @@ SIGNATURES = {
     "damc_round_tf32": (_I, [_P, _P, _SZ, _P]),
     "damc_gemm_tf32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "damc_prior_langevin": (_I, [_P, _P, _I, _I, _F, _I, _P, _U64, _U64, _U64, _P, _P]),
+    "damc_prior_langevin_tc": (_I, [_P, _P, _I, _I, _F, _I, _P, _U64, _U64, _U64, _P]),
     "damc_posterior_langevin": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _U64, _U64, _U64, _P, _P, _P, _SZ, _P]),
     "damc_pack_toy_mlp": (_I, [C.POINTER(_P), _I, _I, _I, C.POINTER(_P), C.POINTER(_P), _P]),
     "damc_toy_posterior_langevin": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, _P, _U64, _U64, _U64, _P]),

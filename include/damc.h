@@ -91,6 +91,12 @@ int damc_prior_langevin(const damc_handle* ebm, float* z, int B, int K, float st
                         const float* noise, uint64_t seed, uint64_t chain0, uint64_t step0, float* trace,
                         void* stream);
 
+/* The same K-step loop with the MLP's four mat-mat products on the tensor cores (fp16 operands, fp32 accumulation and update),
+ * one CTA per 128 chains, all K steps in one launch: the large-batch form (16 384 chains x 60 steps: 1.x ms vs 15.7 ms), at
+ * 16-bit accuracy of dE/dz (csrc/ebm_tc.cu).  No trace.  nz % 4 == 0, nz <= 128, ndf <= 256.                                    */
+int damc_prior_langevin_tc(const damc_handle* ebm, float* z, int B, int K, float step_size, int with_noise, const float* noise,
+                           uint64_t seed, uint64_t chain0, uint64_t step0, void* stream);
+
 /* ---- posterior Langevin  (replaces sample_langevin_post_z_with_prior, reference src/MCMC.py:48-74) -------------
  * U(z) = |G(z)-x|^2/(2 sigma^2) + E(z) + |z|^2/2 ;  ebm may be NULL (toy-style target without the EBM term).
  * trace : NULL, or [K,4] receiving (sum E, |G(z)-x|^2/(2 sigma^2), |z|^2/2, mean(grad)) per step (:65-67).

@@ -217,3 +217,32 @@ def test_posterior_with_tensor_core_ebm_tail_matches_cuda_core_tail(prec, tol, d
     ref = O.langevin_posterior(z0.double(), x.double(), gen64, ebm64, K, sigma, True, 0.1, noise.double())
     a = _with_ebm_tc("1", lambda: run(noise=noise.to(dev)))
     assert float((a - ref).abs().max() / ref.abs().max()) < (2e-2 if prec == "bf16" else 4e-3)
+
+
+def test_prior_langevin_on_tensor_cores(dev):
+    """sample_langevin_prior_z(precision='fp16') -- all K steps in one launch of ebm_tc_step_kernel, MLP products on the tensor
+    cores -- against the fp32 persistent kernel and the fp64 oracle (reference MCMC.py:27-46): injected noise, ragged batch (three
+    tiles, the last one partly empty).  Per-chain bound on the median and on the tail (LeakyReLU kink flips, see
+    test_ebm_gradient_on_tensor_cores); Philox runs must consume the same draws as the fp32 kernel."""
+    from damc_b200 import MCMC, diffusion_net as dn
+    nz, B, K, s = 128, 300, 20, 0.4
+    E = dn._netE(nz)
+    esd = synth.ebm_state(nz)
+    E.load_state_dict(esd)
+    E = E.to(dev)
+    z0, noise = synth.det_normal("pz0", (B, nz)), synth.det_normal("pn", (K, B, nz))
+    ref = O.langevin_prior_analytic(z0.double(), synth.ebm_list_from_state(esd, torch.float64), K, s, True, noise.double())
+    run = lambda **kw: MCMC.sample_langevin_prior_z(z0.to(dev).clone().requires_grad_(True), E, K, s, True, **kw).cpu().double()
+    z32, z16 = run(noise=noise.to(dev)), run(noise=noise.to(dev), precision="fp16")
+    per32 = ((z32 - ref).abs().amax(1) / ref.abs().amax(1)).numpy()
+    per16 = ((z16 - ref).abs().amax(1) / ref.abs().amax(1)).numpy()
+    print(f"prior K={K}: per-chain err vs fp64  fp32 kernel max {per32.max():.2e};  tensor cores median {np.median(per16):.2e} "
+          f"p95 {np.quantile(per16, 0.95):.2e} max {per16.max():.2e}")
+    assert per32.max() < 1e-4
+    assert np.median(per16) < 2e-3 and np.quantile(per16, 0.95) < 3e-2 and per16.max() < 0.2
+    a, b = run(seed=9, chain0=3, step0=1), run(seed=9, chain0=3, step0=1, precision="fp16")   # same Philox draws
+    d = ((a - b).abs().amax(1) / a.abs().amax(1)).numpy()
+    assert np.median(d) < 2e-3 and not torch.equal(a, b)
+    assert torch.equal(b, run(seed=9, chain0=3, step0=1, precision="fp16"))                  # deterministic
+    with pytest.raises(RuntimeError):
+        MCMC.sample_langevin_prior_z(z0.to(dev).clone().requires_grad_(True), E, 2, s, True, True, precision="fp16")
