@@ -22,6 +22,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "damc_common.cuh"
 #include "damc_internal.h"
 #include "tc_ptx.cuh"
@@ -408,12 +410,13 @@ int launch_ebm_step_tc(const MlpPack* m, int precision, float* z, int B, float s
   a.idesc_h = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(ET_H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   a.idesc_z = (1u << 4) | (opfmt << 7) | (opfmt << 10) | ((uint32_t)(t->nzp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const size_t smem = 8 * ET_TILE + ET_STAGES * ET_WSTAGE + 3 * ET_H * 4 + 8 * (2 * ET_STAGES + 2) + 16 + 1024;
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64];   // the dynamic-smem opt-in is a per-device function attribute (idempotent if two threads race)
   int dev = 0;
   DAMC_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  if (dev < 0 || dev >= 64) DAMC_FAIL(DAMC_ERR_UNSUPPORTED, "EBM tensor-core step: device ordinal %d out of range", dev);
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
     DAMC_CUDA(cudaFuncSetAttribute(ebm_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done[dev] = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
