@@ -276,6 +276,8 @@ constexpr int DEN_MAXW = 512;     // widest layer input (concat of two 64*nf hal
 // tcgen05 operands of one precision (bf16 | fp16): per layer one K-major weight matrix [4*dout][din+dout] whose rows are
 // grouped per N tile as [gate | hyper-bias | main | skip] blocks of BN/4 features; one copy per tile width in use.
 constexpr int DEN_NBN = 3;   // tile widths 256, 128, 64
+struct DenSeqPack;           // weights of the hoisted-context schedule (denoiser_seq.cu)
+void den_seq_free(DenSeqPack* p);
 struct DenTcPack {
   void* slab = nullptr;
   void* Wq[DEN_NBN][DEN_LAYERS];  // [bn index][layer]: [4*dout][din+dout] operand type
@@ -288,6 +290,7 @@ struct DenTcPack {
   cudaStream_t cap_stream = nullptr;   // private stream the sequence is captured on (the caller's may be the legacy stream)
   struct GraphKey { int B, T, use_philox; void* ws_base; unsigned long long chain0, coef_hash; } gkey = {0, 0, 0, nullptr, 0, 0};
   int gkey_seen = 0;   // calls with gkey so far (the graph is captured on the second one)
+  DenSeqPack* seq = nullptr;   // built on first use by den_seq_run, kept fresh by den_tc_refill
 };
 
 struct DenPack : damc_handle {
@@ -317,6 +320,11 @@ struct DenWs {   // carved out of the caller's workspace
   void* A[DEN_LAYERS];   // tcgen05 mode: layer operands [B][din+dout] (operand type); null in fp32 mode
   float* zbuf;           // tcgen05 mode: [B][nz] staging copy of z for graph replays
   unsigned long long* seed_dev;
+  // hoisted-context schedule (denoiser_seq.cu): gate / hyper-bias words of a window of steps, U-net skips of layers 0 / 1
+  void* G;               // [window][B^128][csum] half2
+  void* skip[2];         // [B^128][dout] operand type
+  void* nbuf;            // [window][B^128][nz] fp32 normals of the window's steps, tile-transposed
+  void* zT;              // [B^128][nz] fp32 z between the steps of a window, tile-transposed
   void* base;
   size_t bytes;
 };
@@ -337,5 +345,13 @@ int den_cluster_run(const DenPack* d, int precision, const DenWs& w, float* z, f
 int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float* eps_out, int B, int T, int nsteps,
                const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                cudaStream_t stream);
+// denoiser_seq.cu: gate / hyper-bias of all layers hoisted out of the step loop (one parallel pass per window of steps), then ONE
+// CTA per 128 chains runs every step of the window with the activations resident in shared memory
+bool den_seq_shape_ok(const DenPack* d);    // the U-net widths the kernel's buffer plan is written for (sizes the workspace)
+bool den_seq_supported(const DenPack* d);   // shape ok and not switched off (DAMC_DEN_SEQ=0)
+int den_seq_window(int B, int T, int csum); // steps per window
+int den_seq_refill(const DenPack* d, int precision, cudaStream_t stream, const int* dirty);
+int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B, int T, int nsteps, const float* host_coef,
+                const float* noise, int use_philox, uint64_t seed, uint64_t chain0, cudaStream_t stream);
 
 }  // namespace damc

@@ -419,6 +419,14 @@ DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base) {
     w.A[i] = is_tc_precision(precision) ? (void*)take(2 * (size_t)B * (d->din[i] + d->dout[i])) : nullptr;
   w.zbuf = is_tc_precision(precision) ? take(sizeof(float) * (size_t)B * d->nz) : nullptr;
   w.seed_dev = is_tc_precision(precision) ? (unsigned long long*)take(16) : nullptr;
+  if (is_tc_precision(precision) && den_seq_shape_ok(d)) {
+    const size_t bp = align_up((size_t)B, 128);
+    w.skip[0] = take(2 * bp * d->dout[0]);
+    w.skip[1] = take(2 * bp * d->dout[1]);
+    w.G = take(4 * bp * d->csum * (size_t)den_seq_window(B, T, d->csum));
+    w.nbuf = take(4 * bp * d->nz * (size_t)den_seq_window(B, T, d->csum));
+    w.zT = take(4 * bp * d->nz);
+  }
   w.base = base;
   w.bytes = o;
   return w;

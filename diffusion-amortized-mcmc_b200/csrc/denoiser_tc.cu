@@ -56,6 +56,7 @@ void den_tc_free(DenTcPack* t) {
   if (t->gexec) cudaGraphExecDestroy(t->gexec);
   if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
   if (t->slab) cudaFree(t->slab);
+  den_seq_free(t->seq);
   delete t;
 }
 
@@ -95,7 +96,7 @@ int den_tc_refill(const DenPack* d, int precision, cudaStream_t s, const int* di
   for (int i = 0; i < DEN_LAYERS; ++i)
     pack_den_bias4<<<ceil_div(d->dout[i], 128), 128, 0, s>>>(h->b[i], h->bs[i], h->bg[i], d->dout[i], t->bias4[i], dirty);
   DAMC_CUDA(cudaGetLastError());
-  return DAMC_OK;
+  return den_seq_refill(d, precision, s, dirty);
 }
 
 int den_tc_ensure(const DenPack* d, int precision, cudaStream_t s) {
@@ -311,6 +312,8 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
                const float* host_coef, const float* noise, int use_philox, uint64_t seed, uint64_t chain0,
                cudaStream_t s) {
   DAMC_TRY(den_tc_ensure(d, precision, s));
+  if (eps_out == nullptr && w.G && den_seq_supported(d))   // sampler loop: hoisted-context schedule (denoiser_seq.cu)
+    return den_seq_run(d, precision, w, z, B, T, nsteps, host_coef, noise, use_philox, seed, chain0, s);
   if (den_cluster_supported(d, B))   // one launch for all T steps: 4-CTA clusters own 128 chains each (denoiser_cluster.cu)
     return den_cluster_run(d, precision, w, z, eps_out, B, T, nsteps, host_coef, noise, use_philox, seed, chain0, s);
   DenTcPack* t = d->tc[precision];

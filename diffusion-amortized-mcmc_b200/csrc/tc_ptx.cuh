@@ -229,11 +229,25 @@ __device__ __forceinline__ uint32_t pack2(bool fp16, float a, float b) { return 
 // denoiser branch from the four column blocks of the accumulator; bias quads (bg, 0, b, bs) per feature sit in smem.
 // last layer, 4 features [f0, f0+4) of chain r.b:  eps = z + out (residual, :530-531); x0 prediction and ancestral update
 // of z (:610-620), fp32 throughout
-__device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, const float outv[4]) {
+// den_final_math: the arithmetic on loaded operands; den_final_vals: loads + arithmetic (res = new z, or eps when d.eps_out is
+// set); den_final_quad: the same + the store
+__device__ __forceinline__ void den_final_math(const DenEpi& d, const float zt[4], const float nrm[4], bool noisy, const float outv[4],
+                                               float res[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    // explicit rounding points: every tcgen05 schedule (per-layer launches, cluster kernel, hoisted schedule) inlines this
+    // function, and a chain's result must not depend on FMA contractions the compiler would otherwise pick per call site
+    const float eps = d.residual ? __fadd_rn(zt[q], outv[q]) : outv[q];
+    const float pred = __fmul_rn(d.c_pred, fmaf(-eps, d.c_eps, zt[q]));
+    float zn = d.last ? pred : fmaf(d.c_zt, zt[q], __fmul_rn(d.c_x, pred));
+    if (noisy) zn = fmaf(d.c_std, nrm[q], zn);
+    res[q] = d.eps_out ? eps : zn;
+  }
+}
+__device__ __forceinline__ void den_final_vals(const DenEpi& d, int b, int f0, const float outv[4], float res[4]) {
   const long long zi = (long long)b * d.nz + f0;
   const float4 z4 = *reinterpret_cast<const float4*>(d.z + zi);
   const float zt[4] = {z4.x, z4.y, z4.z, z4.w};
-  float res[4];
   float nrm[4] = {0.f, 0.f, 0.f, 0.f};
   const bool noisy = d.eps_out == nullptr && !d.last && d.c_std != 0.f;
   if (noisy) {
@@ -244,16 +258,12 @@ __device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, c
       philox_normal4(d.seed_ptr ? *d.seed_ptr : d.seed, d.chain0 + (unsigned long long)b, d.step, (uint32_t)(f0 >> 2), nrm);
     }
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    // explicit rounding points: both tcgen05 schedules (per-layer launches, cluster kernel) inline this function, and a
-    // chain's result must not depend on which one ran (the compiler would otherwise pick FMA contractions per call site)
-    const float eps = d.residual ? __fadd_rn(zt[q], outv[q]) : outv[q];
-    const float pred = __fmul_rn(d.c_pred, fmaf(-eps, d.c_eps, zt[q]));
-    float zn = d.last ? pred : fmaf(d.c_zt, zt[q], __fmul_rn(d.c_x, pred));
-    if (noisy) zn = fmaf(d.c_std, nrm[q], zn);
-    res[q] = d.eps_out ? eps : zn;
-  }
+  den_final_math(d, zt, nrm, noisy, outv, res);
+}
+__device__ __forceinline__ void den_final_quad(const DenEpi& d, int b, int f0, const float outv[4]) {
+  const long long zi = (long long)b * d.nz + f0;
+  float res[4];
+  den_final_vals(d, b, f0, outv, res);
   float* dstp = d.eps_out ? d.eps_out + zi : d.z + zi;
   *reinterpret_cast<float4*>(dstp) = make_float4(res[0], res[1], res[2], res[3]);
 }
