@@ -47,7 +47,8 @@ struct SqTile {
   unsigned short wrow0, wrows;
   unsigned char oblk, defer, skipsel, commit_ldone;
   unsigned char stage_nblk, stage_blk0, stage_map, layer_last;
-  unsigned short stage_col0, goff, ocol0, gfence;
+  unsigned short stage_col0, goff, ocol0;
+  unsigned char gfence, xcommit;   // xcommit: arrive on bar_xfree once the MMAs of the first `xcommit` k-blocks are complete
 };
 
 struct SqParams {
@@ -107,8 +108,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
   auto bar_hready = [&](int s) { return bars + 8u * (2 * SQ_STAGES + 4 + s); };
   auto bar_cready = [&](int s) { return bars + 8u * (2 * SQ_STAGES + 6 + s); };
   const uint32_t bar_stg = bars + 8u * (2 * SQ_STAGES + 8), bar_ldone = bars + 8u * (2 * SQ_STAGES + 9);
-  const uint32_t tmem_slot = bars + 8u * (2 * SQ_STAGES + 10);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + off_bars + 8u * (2 * SQ_STAGES + 10));
+  const uint32_t bar_xfree = bars + 8u * (2 * SQ_STAGES + 10);
+  const uint32_t tmem_slot = bars + 8u * (2 * SQ_STAGES + 11);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + off_bars + 8u * (2 * SQ_STAGES + 11));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
     }
     mbar_init(bar_stg, 1);
     mbar_init(bar_ldone, 1);
+    mbar_init(bar_xfree, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
                 umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(bar_wempty(stage));
+            if (T.xcommit && T.xcommit == kb + nsub) umma_commit(bar_xfree);
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
           umma_commit(bar_accfull(as));
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
             if (T.kind == SQ_FINAL) ld_zn(0, zq[0], nq[0]);
             if (P.tlog && blockIdx.x == 0 && st == 1 && threadIdx.x == 64) P.tlog[10 * ti + 5] = sq_now();
             mbar_wait(bar_accfull(as), (cnt >> 1) & 1u);
-            if (T.defer) mbar_wait(bar_accfull(as ^ 1u), ((cnt + 1u) >> 1) & 1u);   // output buffer is still an input of the next tile
+            if (T.defer) mbar_wait(bar_xfree, (uint32_t)st & 1u);   // the output blocks are inputs of the next tile's first k-blocks
             tc_fence_after();
             if (P.tlog && blockIdx.x == 0 && st == 1 && threadIdx.x == 64) P.tlog[10 * ti + 6] = sq_now();
             const bool fin = T.kind == SQ_FINAL;
@@ -404,43 +408,56 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
       // ctx activations of global layer g (item, layer) -> c buffer g & 1 (blocks 4 (g & 1) ...): a warp takes 16 rows, 16 lanes
       // cover the 64 columns of a block row (float4 each), two rows per pass
       uint32_t lcnt = 0;
-      auto produce = [&](int item, int l, uint32_t g) {
-        const int tl = item / tiles_b, ctile = item - tl * tiles_b;
+      // The cx / ct loads of the block after the one being converted are always in flight (a cursor over the flat sequence of
+      // (item, layer, 64-column block)): issued one block at a time they cost one DRAM round trip per block, 22 per item.
+      int c_item = first, c_l = 0, c_j = 0;
+      float4 xn[8], tn;
+      const int c4 = (lane & 15) * 4;
+      auto issue = [&]() {
+        if (c_item >= nitems) return;
+        const int ctile = c_item / P.nsteps, tl = c_item - ctile * P.nsteps;
         const int irev = P.T - 1 - (P.s0 + tl);
-        const int c4 = (lane & 15) * 4;
+        const int col = P.coff[c_l] + 64 * c_j + c4;
+        tn = __ldg(reinterpret_cast<const float4*>(P.ct + (size_t)irev * P.csum + col));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const long long bb = (long long)ctile * 128 + ew * 16 + 2 * u + (lane >> 4);
+          xn[u] = bb < P.B ? __ldg(reinterpret_cast<const float4*>(P.cx + bb * P.csum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto produce = [&](int l, uint32_t g) {
         const int nb = P.dout[l] >> 6;
         for (int j = 0; j < nb; ++j) {
-          const int col = P.coff[l] + 64 * j + c4;
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(P.ct + (size_t)irev * P.csum + col));
           float4 x4[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int R = ew * 16 + 2 * u + (lane >> 4);
-            const long long bb = (long long)ctile * 128 + R;
-            x4[u] = bb < P.B ? __ldg(reinterpret_cast<const float4*>(P.cx + bb * P.csum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int u = 0; u < 8; ++u) x4[u] = xn[u];
+          const float4 t4 = tn;
+          if (++c_j == (P.dout[c_l] >> 6)) { c_j = 0; if (++c_l == DEN_LAYERS) { c_l = 0; c_item += stride; } }
+          issue();
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int R = ew * 16 + 2 * u + (lane >> 4);
             const float a0 = x4[u].x + t4.x, a1 = x4[u].y + t4.y, a2 = x4[u].z + t4.z, a3 = x4[u].w + t4.w;
-            const float s0 = a0 / (1.f + __expf(-a0)), s1 = a1 / (1.f + __expf(-a1));
-            const float s2 = a2 / (1.f + __expf(-a2)), s3 = a3 / (1.f + __expf(-a3));
+            const float s0 = __fdividef(a0, 1.f + __expf(-a0)), s1 = __fdividef(a1, 1.f + __expf(-a1));
+            const float s2 = __fdividef(a2, 1.f + __expf(-a2)), s3 = __fdividef(a3, 1.f + __expf(-a3));
             const uint32_t dst = blocks + sq_chunk((int)(4u * (g & 1u)) + j, R, c4) + (uint32_t)((c4 & 4) << 1);
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack2(fp16, s0, s1)), "r"(pack2(fp16, s2, s3)) : "memory");
           }
         }
         signal(bar_cready(g & 1u), false);
       };
-      if (first < nitems) produce(first, 0, 0u);
+      issue();
+      if (first < nitems) produce(0, 0u);
       for (int item = first; item < nitems; item += stride) {
-        const int tl = item / tiles_b, ctile = item - tl * tiles_b;
+        // chain tile major: the steps of one chain tile run at about the same time on neighbouring CTAs and share its cx rows in L2
+        const int ctile = item / P.nsteps, tl = item - ctile * P.nsteps;
         const long long brow = (long long)ctile * 128 + r;
         uint4* Gt = P.G + ((size_t)tl * tiles_b + ctile) * (size_t)(P.csum >> 2) * 128 + r;
         int ti = 0;
         for (int l = 0; l < DEN_LAYERS; ++l, ++lcnt) {
           // the next layer's operand (possibly the next item's first) is formed while this layer's MMAs run
-          if (l + 1 < DEN_LAYERS) produce(item, l + 1, lcnt + 1u);
-          else if (item + stride < nitems) produce(item + stride, 0, lcnt + 1u);
+          if (l + 1 < DEN_LAYERS) produce(l + 1, lcnt + 1u);
+          else if (item + stride < nitems) produce(0, lcnt + 1u);
           const int ntl = P.dout[l] >> 7;
           for (int n = 0; n < ntl; ++n, ++ti, ++cnt) {
             const SqTile& T = P.tile[ti];
@@ -693,11 +710,17 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
       t.nkb = 4;
       for (int j = 0; j < 4; ++j) sq_k(t, j, 4 + j, 64 * j, nt == 0 ? (j == 0 ? SQ_W_H0 : j == 2 ? SQ_W_H1 : 0) : 0);
     }
-    for (int nt = 0; nt < 2; ++nt) {   // L4: [X | Y] -> X once both tiles' MMAs are complete
+    for (int nt = 0; nt < 2; ++nt) {   // L4: [X | Y] -> X, tile 0's output once tile 1 has finished reading X
       SqTile& t = layer_tile(4, nt, 2 * nt);
       t.nkb = 8; t.defer = nt == 0; t.commit_ldone = nt == 1;
-      for (int j = 0; j < 4; ++j) sq_k(t, j, 4 + j, 256 + 64 * j, 0);
-      for (int j = 0; j < 4; ++j) sq_k(t, 4 + j, j, 64 * j, nt == 0 ? (j == 0 ? SQ_W_H0 : j == 2 ? SQ_W_H1 : 0) : 0);
+      if (nt == 0) {   // Y (long ready) first, X as L3's epilogues deliver it
+        for (int j = 0; j < 4; ++j) sq_k(t, j, 4 + j, 256 + 64 * j, 0);
+        for (int j = 0; j < 4; ++j) sq_k(t, 4 + j, j, 64 * j, j == 0 ? SQ_W_H0 : j == 2 ? SQ_W_H1 : 0);
+      } else {         // X first: once these four k-blocks are done, tile 0's epilogue may overwrite X0,X1 while the Y part runs
+        for (int j = 0; j < 4; ++j) sq_k(t, j, j, 64 * j, 0);
+        for (int j = 0; j < 4; ++j) sq_k(t, 4 + j, 4 + j, 256 + 64 * j, 0);
+        t.xcommit = 4;
+      }
     }
     {   // L5: [X | skip 1 staged in Y] -> Y0,Y1
       SqTile& t = layer_tile(5, 0, 4);
@@ -728,7 +751,7 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     Gp.ntiles = n;
   }
 
-  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES * SQ_WSTAGE + 8 * (2 * SQ_STAGES + 10) + 16 + 1024;
+  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES * SQ_WSTAGE + 8 * (2 * SQ_STAGES + 11) + 16 + 1024;
   int dev = 0, sms = 148;
   DAMC_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
