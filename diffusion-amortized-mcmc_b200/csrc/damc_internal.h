@@ -325,6 +325,7 @@ struct DenWs {   // carved out of the caller's workspace
   void* skip[2];         // [B^128][dout] operand type
   void* nbuf;            // [window][B^128][nz] fp32 normals of the window's steps, tile-transposed
   void* zT;              // [B^128][nz] fp32 z between the steps of a window, tile-transposed
+  void* xr;              // [B][nxemb] tf32(SiLU(xemb)), the operand of the cx GEMM
   void* base;
   size_t bytes;
 };
@@ -350,6 +351,8 @@ int den_tc_run(const DenPack* d, int precision, const DenWs& w, float* z, float*
 bool den_seq_shape_ok(const DenPack* d);    // the U-net widths the kernel's buffer plan is written for (sizes the workspace)
 bool den_seq_supported(const DenPack* d);   // shape ok and not switched off (DAMC_DEN_SEQ=0)
 int den_seq_window(int B, int T, int csum); // steps per window
+bool den_seq_hoist_usable(const DenPack* d, int precision, int B);
+int den_seq_hoist(const DenPack* d, int precision, const DenWs& w, const float* xemb, int B, cudaStream_t stream);   // cx on the tensor cores
 int den_seq_refill(const DenPack* d, int precision, cudaStream_t stream, const int* dirty);
 int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B, int T, int nsteps, const float* host_coef,
                 const float* noise, int use_philox, uint64_t seed, uint64_t chain0, cudaStream_t stream);

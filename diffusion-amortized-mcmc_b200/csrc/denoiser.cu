@@ -394,11 +394,12 @@ static int launch_den_stream(const DenPack* d, DenStreamArgs& a, int B, cudaStre
 }
 
 static int run_hoist_and_time(const DenPack* d, const float* xemb, int B, int T, const float* host_logsnr, float* cx,
-                              float* ct, float* dlog, cudaStream_t s) {
+                              float* ct, float* dlog, cudaStream_t s, bool hoist = true) {
   DAMC_CUDA(cudaMemcpyAsync(dlog, host_logsnr, sizeof(float) * T, cudaMemcpyHostToDevice, s));
   den_time_kernel<<<T, 256, sizeof(float) * 3 * d->ntemb, s>>>(dlog, d->tw1, d->tb1, d->tw2, d->tb2, d->WcT_t,
                                                              d->ntemb, d->csum, ct);
   DAMC_CUDA(cudaGetLastError());
+  if (!hoist) return DAMC_OK;   // the caller forms cx on the tensor cores (den_seq_hoist)
   const size_t sm = sizeof(float) * d->nxemb * 8;
   DAMC_CUDA(cudaFuncSetAttribute(den_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   den_hoist_kernel<<<dim3(ceil_div(d->csum, 256), ceil_div(B, 8)), 256, sm, s>>>(xemb, d->WcT_x, d->bc, B, d->nxemb,
@@ -426,6 +427,7 @@ DenWs den_ws(const DenPack* d, int B, int T, int precision, void* base) {
     w.G = take(4 * bp * d->csum * (size_t)den_seq_window(B, T, d->csum));
     w.nbuf = take(4 * bp * d->nz * (size_t)den_seq_window(B, T, d->csum));
     w.zT = take(4 * bp * d->nz);
+    w.xr = take(4 * (size_t)B * d->nxemb);
   }
   w.base = base;
   w.bytes = o;
@@ -561,7 +563,9 @@ extern "C" int damc_denoise(const damc_handle* den, float* z, const float* xemb,
   cudaStream_t s = (cudaStream_t)stream;
   const DenWs w = den_ws(d, B, T, precision, workspace);
   if (!workspace || workspace_bytes < w.bytes) DAMC_FAIL(DAMC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
-  DAMC_TRY(run_hoist_and_time(d, xemb, B, T, host_logsnr, w.cx, w.ct, w.dlog, s));
+  const bool tc_hoist = den_seq_hoist_usable(d, precision, B);
+  DAMC_TRY(run_hoist_and_time(d, xemb, B, T, host_logsnr, w.cx, w.ct, w.dlog, s, !tc_hoist));
+  if (tc_hoist) DAMC_TRY(den_seq_hoist(d, precision, w, xemb, B, s));
   std::vector<float> coef(8 * (size_t)T, 0.f);
   for (int k = 0, i = T - 1; i >= 0; --i, ++k) {
     float* c = &coef[8 * (size_t)k];

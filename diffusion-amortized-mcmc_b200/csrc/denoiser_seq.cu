@@ -33,7 +33,9 @@ constexpr int SQ_THREADS = 320;        // warp 0: TMA, warp 1: MMA issuer + TMEM
 constexpr int SQ_BLK = 128 * 128;      // one K-major k-block of a 128-row operand tile (64 columns x 16 bit): 16 KB
 constexpr int SQ_NBLK = 8;             // X = blocks 0-3, Y = blocks 4-7
 constexpr int SQ_WSTAGE = 256 * 128;   // one weight k-block: 256 rows x 128 B
-constexpr int SQ_STAGES = 3;
+constexpr int SQ_STAGES_STEP = 3;   // step pass: the weight stream feeds the chain of dependent MMAs
+constexpr int SQ_STAGES_GATE = 2;   // gate pass: worker-bound; the third stage's room holds the bias table instead
+constexpr int SQ_MAXCSUM = 2048;    // gate pass bias table: 3 x csum floats in shared memory
 constexpr int SQ_MAXKB = 8;
 constexpr int SQ_MAXTILES = 12;
 constexpr int SQ_EMB_MAP = 7;
@@ -41,8 +43,14 @@ enum { SQ_EMB = 0, SQ_LAYER = 1, SQ_FINAL = 2, SQ_GATE = 3 };
 enum { SQ_W_NONE = 0, SQ_W_H0 = 1, SQ_W_H1 = 2, SQ_W_STG = 3, SQ_W_C = 4 };
 
 struct SqK { unsigned char ablk, wait; unsigned short wcol; };
+// U-net skip rows leave by TMA store from the operand blocks the epilogue has just written: issued by the MMA thread after the
+// hready wait of k-block `kb` (two 64-column blocks from `blk0` to columns `col0`, `col0 + 64` of skip tensor `sel`); kb = 255: none
+struct SqSt { unsigned char kb, sel, blk0, col0; };
 struct SqTile {
   SqK k[SQ_MAXKB];
+  SqSt st[2];
+  unsigned char rdwait, fullwait, pad0, pad1;   // before this tile's accumulator commit: rdwait = 1 + N: wait until at most N store
+                                                // groups still read shared memory; fullwait: until every store has completed
   unsigned char nkb, wmap, kind, layer;
   unsigned short wrow0, wrows;
   unsigned char oblk, defer, skipsel, commit_ldone;
@@ -79,12 +87,22 @@ struct SqParams {
   unsigned long long* tlog;   // DAMC_SQ_DBG=1: time stamps of CTA 0, second pass (8 per tile)
 };
 
+static_assert(sizeof(SqParams) <= 4096, "kernel parameter block");
+
 __device__ __forceinline__ unsigned long long sq_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// pull a contiguous global range into L2 (no destination in the SM): the epilogues' per-tile streams are requested only a tile's MMA
+// time before they are needed -- less than a DRAM round trip under load
+__device__ __forceinline__ void sq_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void sq_st16(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -99,7 +117,10 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t blocks = base, ring = base + (uint32_t)SQ_NBLK * SQ_BLK;
-  const uint32_t off_bars = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
+  constexpr int SQ_STAGES = MODE == 0 ? SQ_STAGES_STEP : SQ_STAGES_GATE;
+  const uint32_t off_bias = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
+  const uint32_t off_bars = off_bias + (MODE == 1 ? 3u * SQ_MAXCSUM * 4u : 0u);
+  float* const sbias = reinterpret_cast<float*>(gen_base + off_bias);   // gate pass: [b_main | b_skip | b_gate] x csum
   const uint32_t bars = base + off_bars;
   auto bar_wfull = [&](int s) { return bars + 8u * s; };
   auto bar_wempty = [&](int s) { return bars + 8u * (SQ_STAGES + s); };
@@ -126,6 +147,12 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (MODE == 1)
+    for (int l = 0; l < DEN_LAYERS; ++l)
+      for (int i = threadIdx.x; i < 3 * P.dout[l]; i += SQ_THREADS) {
+        const int k = i / P.dout[l], f = i - k * P.dout[l];
+        sbias[k * P.csum + P.coff[l] + f] = __ldg(P.bias3[l] + i);
+      }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,9 +167,20 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, ldph = 0;
+      auto prefetch_g = [&](int pitem, int pt) {   // gate words of tile pt of step pitem: 128 features x 128 rows, contiguous
+        if (pitem >= nitems || P.tile[pt].kind == SQ_EMB) return;
+        sq_prefetch_l2(P.G + (((size_t)pitem * tiles_b + blockIdx.x) * (size_t)(P.csum >> 2) + (P.tile[pt].goff >> 2)) * 128, 128u * 128u * 4u);
+      };
+      if (MODE == 0) { prefetch_g(0, 1); prefetch_g(0, 2); }
       for (int item = first; item < nitems; item += stride)
         for (int ti = 0; ti < P.ntiles; ++ti) {
           const SqTile& T = P.tile[ti];
+          if (MODE == 0) {   // three tiles ahead; the step's normals half a step ahead
+            const int pt = ti + 3;
+            if (pt < P.ntiles) prefetch_g(item, pt); else prefetch_g(item + 1, pt - P.ntiles);
+            if (ti == 4 && P.noiseT)
+              sq_prefetch_l2(P.noiseT + ((size_t)item * tiles_b + blockIdx.x) * (size_t)(P.nz >> 2) * 128, 128u * (uint32_t)P.nz * 4u);
+          }
           if (MODE == 0 && T.stage_nblk) {   // U-net skip blocks come back from L2 once the buffer they land in is no longer read
             mbar_wait(bar_ldone, ldph);
             ldph ^= 1u;
@@ -190,6 +228,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
             else if (wc == SQ_W_H1) { mbar_wait(bar_hready(1), hph[1]); hph[1] ^= 1u; }
             else if (wc == SQ_W_STG) { mbar_wait(bar_stg, stgph); stgph ^= 1u; }
             else if (wc == SQ_W_C) { mbar_wait(bar_cready(lcnt & 1u), (lcnt >> 1) & 1u); }
+            if (MODE == 0) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                if (T.st[q].kb == kb) {
+                  tma_store_2d(&P.tmSkip[T.st[q].sel], blocks + (uint32_t)T.st[q].blk0 * SQ_BLK, T.st[q].col0, (int)blockIdx.x * 128);
+                  tma_store_2d(&P.tmSkip[T.st[q].sel], blocks + (uint32_t)(T.st[q].blk0 + 1) * SQ_BLK, T.st[q].col0 + 64, (int)blockIdx.x * 128);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
             if (lg && kb == 0) P.tlog[10 * ti + 2] = sq_now();
             mbar_wait(bar_wfull(stage), phase);
             tc_fence_after();
@@ -204,6 +251,11 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
             umma_commit(bar_wempty(stage));
             if (T.xcommit && T.xcommit == kb + nsub) umma_commit(bar_xfree);
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
+          }
+          if (MODE == 0) {   // (the stores were issued microseconds ago: these waits do not stall)
+            if (T.rdwait == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            else if (T.rdwait == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (T.fullwait) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           }
           umma_commit(bar_accfull(as));
           if (lg) P.tlog[10 * ti + 4] = sq_now();
@@ -422,7 +474,10 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const long long bb = (long long)ctile * 128 + ew * 16 + 2 * u + (lane >> 4);
-          xn[u] = bb < P.B ? __ldg(reinterpret_cast<const float4*>(P.cx + bb * P.csum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bb < P.B)   // read once per step: keep it out of L1
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(xn[u].x), "=f"(xn[u].y), "=f"(xn[u].z), "=f"(xn[u].w) : "l"(P.cx + bb * P.csum + col));
         }
       };
       auto produce = [&](int l, uint32_t g) {
@@ -451,7 +506,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
       for (int item = first; item < nitems; item += stride) {
         // chain tile major: the steps of one chain tile run at about the same time on neighbouring CTAs and share its cx rows in L2
         const int ctile = item / P.nsteps, tl = item - ctile * P.nsteps;
-        const long long brow = (long long)ctile * 128 + r;
         uint4* Gt = P.G + ((size_t)tl * tiles_b + ctile) * (size_t)(P.csum >> 2) * 128 + r;
         int ti = 0;
         for (int l = 0; l < DEN_LAYERS; ++l, ++lcnt) {
@@ -465,9 +519,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
             const uint32_t t_acc = t_lane + as * 256u;
             mbar_wait_relaxed(bar_accfull(as), (cnt >> 1) & 1u);
             tc_fence_after();
-            const float* bm = P.bias3[l] + T.ocol0 + half * 64;
-            const float* bs = P.bias3[l] + P.dout[l] + T.ocol0 + half * 64;
-            const float* bg = P.bias3[l] + 2 * P.dout[l] + T.ocol0 + half * 64;
+            const float* bm = sbias + T.goff + half * 64;   // same address in every lane: shared-memory broadcasts
+            const float* bs = bm + P.csum;
+            const float* bg = bs + P.csum;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t vg[16], vh[16];
@@ -477,9 +531,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
               uint32_t w[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(bg + c * 16) + i4);
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(bs + c * 16) + i4);
-                const float4 m4 = __ldg(reinterpret_cast<const float4*>(bm + c * 16) + i4);
+                const float4 g4 = *(reinterpret_cast<const float4*>(bg + c * 16) + i4);
+                const float4 s4 = *(reinterpret_cast<const float4*>(bs + c * 16) + i4);
+                const float4 m4 = *(reinterpret_cast<const float4*>(bm + c * 16) + i4);
                 const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -562,7 +616,25 @@ __global__ void pack_seq_emb(const float* __restrict__ Bp, int nz, __half* __res
   row[k] = h; row[nz + k] = h; row[2 * nz + k] = l;
 }
 
+// K-major tf32-rounded copy [csum][nxemb] of the xemb half of every layer's ctx Linear (Wc[:, ntemb:])
+__global__ void pack_seq_wcx(const float* __restrict__ Wc, int dout, int ntemb, int nxemb, float* __restrict__ dst, const int* __restrict__ dirty) {
+  if (gate_clean(dirty)) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)dout * nxemb) return;
+  const int n = (int)(i / nxemb), k = (int)(i - (long long)n * nxemb);
+  dst[i] = tf32_rna(Wc[(size_t)n * (ntemb + nxemb) + ntemb + k]);
+}
+// the ctx Linear acts on SiLU(xemb) (diffusion_net.py:426: Sequential(SiLU, Linear, SiLU)): operand rows tf32(SiLU(xemb))
+__device__ __forceinline__ float sq_silu(float v) { return v / (1.f + expf(-v)); }
+__global__ void __launch_bounds__(256) sq_silu_tf32(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = src[i];
+  dst[i] = make_float4(tf32_rna(sq_silu(v.x)), tf32_rna(sq_silu(v.y)), tf32_rna(sq_silu(v.z)), tf32_rna(sq_silu(v.w)));
+}
+
 struct DenSeqPack {
+  float* Wcx = nullptr;   // [csum][nxemb] tf32 (own allocation)
   void* slab = nullptr;
   void* Wms[DEN_LAYERS];
   void* Wgh[DEN_LAYERS];
@@ -573,6 +645,7 @@ struct DenSeqPack {
 void den_seq_free(DenSeqPack* p) {
   if (!p) return;
   if (p->slab) cudaFree(p->slab);
+  if (p->Wcx) cudaFree(p->Wcx);
   delete p;
 }
 
@@ -584,7 +657,7 @@ bool den_seq_supported(const DenPack* d) {
 bool den_seq_shape_ok(const DenPack* d) {
   if (d->nz != 128 || d->din[0] != 2 * d->nz || d->dout[6] != d->nz) return false;
   for (int i = 0; i < DEN_LAYERS; ++i)
-    if ((d->dout[i] != 128 && d->dout[i] != 256) || d->csum > 65535) return false;
+    if ((d->dout[i] != 128 && d->dout[i] != 256) || d->csum > SQ_MAXCSUM) return false;
   // U-net wiring this kernel's buffer plan is written for (diffusion_net.py:505-528): 128 -> 256 -> 256 | 256 | (256+256) -> 256,
   // (256+256) -> 128, (128+128) -> nz
   return d->dout[0] == 128 && d->dout[1] == 256 && d->dout[2] == 256 && d->dout[3] == 256 && d->dout[4] == 256 && d->dout[5] == 128 &&
@@ -608,6 +681,9 @@ int den_seq_refill(const DenPack* d, int precision, cudaStream_t s, const int* d
     }
   }
   pack_seq_emb<<<ceil_div((d->nz / 2) * d->nz, 256), 256, 0, s>>>(h->Bproj, d->nz, p->Wemb, dirty);
+  for (int i = 0; i < DEN_LAYERS; ++i)
+    pack_seq_wcx<<<(unsigned)(((long long)d->dout[i] * d->nxemb + 255) / 256), 256, 0, s>>>(h->Wc[i], d->dout[i], d->ntemb, d->nxemb,
+                                                                                              p->Wcx + (size_t)d->coff[i] * d->nxemb, dirty);
   DAMC_CUDA(cudaGetLastError());
   return DAMC_OK;
 }
@@ -632,9 +708,37 @@ static int den_seq_ensure(const DenPack* d, int precision, cudaStream_t s) {
   }
   p->Wemb = (__half*)q;
   if (r == DAMC_OK) r = tc_encode_2d(&p->tmEmb, 1, p->Wemb, 3 * d->nz, d->nz / 2, d->nz / 2);
+  if (r == DAMC_OK && cudaMalloc(&p->Wcx, sizeof(float) * (size_t)d->csum * d->nxemb) != cudaSuccess) { r = DAMC_ERR_CUDA; set_error("denoiser (hoisted schedule): cudaMalloc failed"); }
   if (r != DAMC_OK) { den_seq_free(p); return r; }
   t->seq = p;
   return den_seq_refill(d, precision, s, nullptr);
+}
+
+// cx = SiLU(xemb) Wc_x^T + bc for all layers (diffusion_net.py:426-433, the xemb half of the ctx Linears) as ONE tcgen05 GEMM in TF32
+// (operands rounded, not truncated) instead of the CUDA-core hoist kernel: 47 GFLOP at 16 384 chains, 3 ms -> 0.1 ms
+bool den_seq_hoist_usable(const DenPack* d, int precision, int B) {
+  (void)B;   // every batch size: a chain's result must not depend on how the batch is sharded
+  return is_tc_precision(precision) && d->nxemb % 32 == 0 && d->csum % 16 == 0 && den_seq_supported(d);
+}
+int den_seq_hoist(const DenPack* d, int precision, const DenWs& w, const float* xemb, int B, cudaStream_t s) {
+  DAMC_TRY(den_seq_ensure(d, precision, s));
+  const DenSeqPack* p = d->tc[precision]->seq;
+  if (!w.xr) DAMC_FAIL(DAMC_ERR_WORKSPACE, "denoiser (hoisted schedule): workspace was carved without the xemb copy");
+  if ((uintptr_t)xemb & 15) DAMC_FAIL(DAMC_ERR_INVALID, "denoiser: xemb must be 16-byte aligned");
+  const size_t n4 = (size_t)B * d->nxemb / 4;
+  sq_silu_tf32<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(xemb), reinterpret_cast<float4*>(w.xr), n4);
+  DAMC_CUDA(cudaGetLastError());
+  GemmPlan g{};
+  g.A = w.xr; g.B = B; g.Hm = 1; g.Wm = 1; g.Cs = d->nxemb;
+  g.ntaps = 1; g.taps[0] = Tap{0, 0, 0, 0};
+  g.N = g.Np = d->csum; g.ksplit = 1;
+  g.Wtc = p->Wcx;
+  g.epi.kind = EPI_STORE_F32_BIAS;
+  g.epi.bias = d->bc;
+  g.epi.out = w.cx;
+  g.epi.nz_out = d->csum;
+  count_launch(2);
+  return launch_gemm_tc(g, DAMC_PREC_TF32, s);
 }
 
 // steps per window: the gate pass writes G for this many steps, then the step pass consumes them
@@ -676,6 +780,10 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
   DAMC_TRY(tc_encode_2d(&S.tmSkip[1], fp16, w.skip[1], d->dout[1], Bpad, 128));
 
   // ---- step-pass program (buffer plan in the header comment; X = blocks 0-3, Y = 4-7) ----
+  const char* ets = getenv("DAMC_SQ_TMASTORE");   // experiment switch: 0 = the epilogue threads store the skip rows themselves
+  const bool tma_store = !(ets && ets[0] == '0');
+  for (SqTile& t : S.tile) t.st[0].kb = t.st[1].kb = 255;
+  for (SqTile& t : Gp.tile) t.st[0].kb = t.st[1].kb = 255;
   {
     int n = 0;
     auto layer_tile = [&](int l, int nt, int oblk) -> SqTile& {
@@ -692,22 +800,24 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     }
     {   // L0: X0-3 -> Y0,Y1 (+ skip 0)
       SqTile& t = layer_tile(0, 0, 4);
-      t.nkb = 4; t.skipsel = 1;
+      t.nkb = 4; t.skipsel = tma_store ? 0 : 1;
       for (int j = 0; j < 4; ++j) sq_k(t, j, (!fp16 && j >= 2) ? 4 + j : j, 64 * j, j == 0 ? SQ_W_H0 : 0);   // bf16: z columns sit in Y2,Y3
     }
     for (int nt = 0; nt < 2; ++nt) {   // L1: Y0,Y1 -> X (+ skip 1)
       SqTile& t = layer_tile(1, nt, 2 * nt);
-      t.nkb = 2; t.skipsel = 2;
+      t.nkb = 2; t.skipsel = tma_store ? 0 : 2;
       for (int j = 0; j < 2; ++j) sq_k(t, j, 4 + j, 64 * j, (nt == 0 && j == 0) ? SQ_W_H1 : 0);
+      if (tma_store && nt == 0) t.st[0] = SqSt{0, 0, 4, 0};   // L0's output (Y0,Y1) is complete once hready[1] has been waited for
     }
     for (int nt = 0; nt < 2; ++nt) {   // L2: X -> Y (stays resident: it is also the skip of L4)
       SqTile& t = layer_tile(2, nt, 4 + 2 * nt);
-      t.nkb = 4; t.gfence = nt == 0;   // the skip rows of L0 / L1 left this thread long ago: one cheap all-spaces proxy fence here
+      t.nkb = 4; t.gfence = nt == 0 && !tma_store;   // (thread-stored skip rows: one all-spaces proxy fence, long after the stores)
+      if (tma_store && nt == 0) { t.st[0] = SqSt{0, 1, 0, 0}; t.st[1] = SqSt{2, 1, 2, 128}; t.rdwait = 3; }   // L1's halves; Y0,Y1 are rewritten next
       for (int j = 0; j < 4; ++j) sq_k(t, j, j, 64 * j, nt == 0 ? (j == 0 ? SQ_W_H0 : j == 2 ? SQ_W_H1 : 0) : 0);
     }
     for (int nt = 0; nt < 2; ++nt) {   // L3: Y -> X
       SqTile& t = layer_tile(3, nt, 2 * nt);
-      t.nkb = 4;
+      t.nkb = 4; t.rdwait = (tma_store && nt == 0) ? 1 : 0;   // X is rewritten by this layer's epilogues
       for (int j = 0; j < 4; ++j) sq_k(t, j, 4 + j, 64 * j, nt == 0 ? (j == 0 ? SQ_W_H0 : j == 2 ? SQ_W_H1 : 0) : 0);
     }
     for (int nt = 0; nt < 2; ++nt) {   // L4: [X | Y] -> X, tile 0's output once tile 1 has finished reading X
@@ -719,7 +829,7 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
       } else {         // X first: once these four k-blocks are done, tile 0's epilogue may overwrite X0,X1 while the Y part runs
         for (int j = 0; j < 4; ++j) sq_k(t, j, j, 64 * j, 0);
         for (int j = 0; j < 4; ++j) sq_k(t, 4 + j, 4 + j, 256 + 64 * j, 0);
-        t.xcommit = 4;
+        t.xcommit = 4; t.fullwait = tma_store;   // the skip rows are in L2 before `ldone` lets the TMA loads fetch them back
       }
     }
     {   // L5: [X | skip 1 staged in Y] -> Y0,Y1
@@ -751,12 +861,13 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     Gp.ntiles = n;
   }
 
-  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES * SQ_WSTAGE + 8 * (2 * SQ_STAGES + 11) + 16 + 1024;
+  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_STEP * SQ_WSTAGE + 8 * (2 * SQ_STAGES_STEP + 11) + 16 + 1024;
+  const size_t smem_g = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_GATE * SQ_WSTAGE + 3 * SQ_MAXCSUM * 4 + 8 * (2 * SQ_STAGES_GATE + 11) + 16 + 1024;
   int dev = 0, sms = 148;
   DAMC_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   DAMC_CUDA(cudaFuncSetAttribute(den_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DAMC_CUDA(cudaFuncSetAttribute(den_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DAMC_CUDA(cudaFuncSetAttribute(den_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   static unsigned long long* tlog = nullptr;
   const bool dbg = getenv("DAMC_SQ_DBG") != nullptr;
   if (dbg && !tlog) { cudaMalloc(&tlog, 128 * 8); }
@@ -777,7 +888,7 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
       count_launch();
     }
     profile_mark(s, true);
-    den_seq_kernel<1><<<std::min(items, sms), SQ_THREADS, smem, s>>>(Gp);
+    den_seq_kernel<1><<<std::min(items, sms), SQ_THREADS, smem_g, s>>>(Gp);
     profile_mark(s, false);
     profile_mark(s, true);
     den_seq_kernel<0><<<Bpad / 128, SQ_THREADS, smem, s>>>(S);
