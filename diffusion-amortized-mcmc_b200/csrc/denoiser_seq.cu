@@ -30,12 +30,14 @@
 namespace damc {
 
 constexpr int SQ_THREADS = 320;        // warp 0: TMA, warp 1: MMA issuer + TMEM, warps 2-9: workers (two per TMEM lane quarter)
+constexpr int SQ_GATE_PW = 8;          // gate pass: producer warps (warps 10 ...) that form the ctx operand tiles, 128 / SQ_GATE_PW chain rows each
+constexpr int SQ_THREADS_GATE = 320 + 32 * SQ_GATE_PW;
 constexpr int SQ_BLK = 128 * 128;      // one K-major k-block of a 128-row operand tile (64 columns x 16 bit): 16 KB
 constexpr int SQ_NBLK = 8;             // X = blocks 0-3, Y = blocks 4-7
 constexpr int SQ_WSTAGE = 256 * 128;   // one weight k-block: 256 rows x 128 B
 constexpr int SQ_STAGES_STEP = 3;   // step pass: the weight stream feeds the chain of dependent MMAs
-constexpr int SQ_STAGES_GATE = 2;   // gate pass: worker-bound; the third stage's room holds the bias table instead
-constexpr int SQ_MAXCSUM = 2048;    // gate pass bias table: 3 x csum floats in shared memory
+constexpr int SQ_STAGES_GATE = 3;   // (two stages leave the gate pass bound by the ~2 us a 256-row weight box takes to arrive)
+constexpr int SQ_MAXCSUM = 65535;   // tile offsets are 16-bit
 constexpr int SQ_MAXKB = 8;
 constexpr int SQ_MAXTILES = 12;
 constexpr int SQ_EMB_MAP = 7;
@@ -111,16 +113,14 @@ __device__ __forceinline__ uint32_t sq_chunk(int blk, int r, int col) {
   return (uint32_t)blk * SQ_BLK + (uint32_t)r * 128u + (uint32_t)((((col & 63) >> 3) ^ (r & 7)) << 4);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_constant__ SqParams P) {
+template <int MODE, bool FP16>   // FP16: operand type fp16 (else bf16), a compile-time constant in every conversion
+__global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) den_seq_kernel(const __grid_constant__ SqParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t blocks = base, ring = base + (uint32_t)SQ_NBLK * SQ_BLK;
   constexpr int SQ_STAGES = MODE == 0 ? SQ_STAGES_STEP : SQ_STAGES_GATE;
-  const uint32_t off_bias = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
-  const uint32_t off_bars = off_bias + (MODE == 1 ? 3u * SQ_MAXCSUM * 4u : 0u);
-  float* const sbias = reinterpret_cast<float*>(gen_base + off_bias);   // gate pass: [b_main | b_skip | b_gate] x csum
+  const uint32_t off_bars = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
   const uint32_t bars = base + off_bars;
   auto bar_wfull = [&](int s) { return bars + 8u * s; };
   auto bar_wempty = [&](int s) { return bars + 8u * (SQ_STAGES + s); };
@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
   auto bar_cready = [&](int s) { return bars + 8u * (2 * SQ_STAGES + 6 + s); };
   const uint32_t bar_stg = bars + 8u * (2 * SQ_STAGES + 8), bar_ldone = bars + 8u * (2 * SQ_STAGES + 9);
   const uint32_t bar_xfree = bars + 8u * (2 * SQ_STAGES + 10);
-  const uint32_t tmem_slot = bars + 8u * (2 * SQ_STAGES + 11);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + off_bars + 8u * (2 * SQ_STAGES + 11));
+  auto bar_cfree = [&](int s) { return bars + 8u * (2 * SQ_STAGES + 11 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * SQ_STAGES + 13);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + off_bars + 8u * (2 * SQ_STAGES + 13));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -139,7 +140,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
     if (MODE == 0) { prefetch_tmap(&P.tmSkip[0]); prefetch_tmap(&P.tmSkip[1]); }
     for (int s = 0; s < SQ_STAGES; ++s) { mbar_init(bar_wfull(s), 1); mbar_init(bar_wempty(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), 8); mbar_init(bar_hready(s), 8); mbar_init(bar_cready(s), 8);
+      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), 8); mbar_init(bar_hready(s), 8); mbar_init(bar_cready(s), SQ_GATE_PW);
+      mbar_init(bar_cfree(s), 1);
     }
     mbar_init(bar_stg, 1);
     mbar_init(bar_ldone, 1);
@@ -147,12 +149,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (MODE == 1)
-    for (int l = 0; l < DEN_LAYERS; ++l)
-      for (int i = threadIdx.x; i < 3 * P.dout[l]; i += SQ_THREADS) {
-        const int k = i / P.dout[l], f = i - k * P.dout[l];
-        sbias[k * P.csum + P.coff[l] + f] = __ldg(P.bias3[l] + i);
-      }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -260,15 +256,71 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
           umma_commit(bar_accfull(as));
           if (lg) P.tlog[10 * ti + 4] = sq_now();
           if (T.commit_ldone) umma_commit(bar_ldone);
+          if (MODE == 1 && T.layer_last) umma_commit(bar_cfree(lcnt & 1u));   // the ctx buffer of this layer may be rewritten
           if (T.layer_last) ++lcnt;
           ++cnt;
         }
     }
+  } else if (MODE == 1 && warp >= 10) {
+    // ===================== gate pass, 4 producer warps: ctx activations c = SiLU(cx[b] + ct[t]) of global layer g (item, layer) ->
+    // c buffer g & 1 (blocks 4 (g & 1) ...).  A warp owns 32 chain rows; 16 lanes cover the 64 columns of a block row (float4
+    // each), two rows per instruction, 16 rows per pass.  The cx / ct loads of the pass after the one being converted are always
+    // in flight (a cursor over the flat sequence of (item, layer, 64-column block, half)): issued one pass at a time they would
+    // cost a DRAM round trip per pass.
+    const int pw = warp - 10;
+    constexpr bool fp16 = FP16;
+    constexpr int PROWS = 128 / SQ_GATE_PW, PH = PROWS / 16;   // rows per producer warp, 16-row passes per block
+    int c_item = first, c_l = 0, c_j = 0, c_h = 0;
+    float4 xn[8], tn;
+    const int c4 = (lane & 15) * 4;
+    auto issue = [&]() {
+      if (c_item >= nitems) return;
+      const int ctile = c_item / P.nsteps, tl = c_item - ctile * P.nsteps;
+      const int irev = P.T - 1 - (P.s0 + tl);
+      const int col = P.coff[c_l] + 64 * c_j + c4;
+      tn = __ldg(reinterpret_cast<const float4*>(P.ct + (size_t)irev * P.csum + col));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long bb = (long long)ctile * 128 + pw * PROWS + c_h * 16 + 2 * u + (lane >> 4);
+        xn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bb < P.B)   // read once per step: keep it out of L1
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(xn[u].x), "=f"(xn[u].y), "=f"(xn[u].z), "=f"(xn[u].w) : "l"(P.cx + bb * P.csum + col));
+      }
+    };
+    issue();
+    uint32_t g = 0;
+    for (int item = first; item < nitems; item += stride)
+      for (int l = 0; l < DEN_LAYERS; ++l, ++g) {
+        if (g >= 2) mbar_wait_relaxed(bar_cfree(g & 1u), ((g >> 1) - 1u) & 1u);   // the MMAs of layer g - 2 have read this buffer
+        const int nb = P.dout[l] >> 6;
+        for (int j = 0; j < nb; ++j)
+          for (int h = 0; h < PH; ++h) {
+            float4 x4[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x4[u] = xn[u];
+            const float4 t4 = tn;
+            if (++c_h == PH) { c_h = 0; if (++c_j == (P.dout[c_l] >> 6)) { c_j = 0; if (++c_l == DEN_LAYERS) { c_l = 0; c_item += stride; } } }
+            issue();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int R = pw * PROWS + h * 16 + 2 * u + (lane >> 4);
+              const float a0 = x4[u].x + t4.x, a1 = x4[u].y + t4.y, a2 = x4[u].z + t4.z, a3 = x4[u].w + t4.w;
+              const float s0 = __fdividef(a0, 1.f + __expf(-a0)), s1 = __fdividef(a1, 1.f + __expf(-a1));
+              const float s2 = __fdividef(a2, 1.f + __expf(-a2)), s3 = __fdividef(a3, 1.f + __expf(-a3));
+              const uint32_t dst = blocks + sq_chunk((int)(4u * (g & 1u)) + j, R, c4) + (uint32_t)((c4 & 4) << 1);
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack2(fp16, s0, s1)), "r"(pack2(fp16, s2, s3)) : "memory");
+            }
+          }
+        fence_proxy_async();   // generic-proxy writes of the tile -> the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cready(g & 1u));
+      }
   } else {
     // ===================== 8 worker warps: two per TMEM lane quarter; a thread owns one chain row and half of a tile's features ====
     const int ew = warp - 2, q = warp & 3, half = ew >> 2, r = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool fp16 = P.fp16 != 0;
+    constexpr bool fp16 = FP16;
     // this warp's part of an operand tile is written (generic proxy): hand it to the async proxy.  all_spaces: also the skip rows
     // this thread stored to global memory since the last such fence (read back by TMA much later)
     auto signal = [&](uint32_t bar, bool all_spaces) {
@@ -457,61 +509,13 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
       }
     } else {
       // ---------------------------------------------- gate pass ----------------------------------------------------------------
-      // ctx activations of global layer g (item, layer) -> c buffer g & 1 (blocks 4 (g & 1) ...): a warp takes 16 rows, 16 lanes
-      // cover the 64 columns of a block row (float4 each), two rows per pass
-      uint32_t lcnt = 0;
-      // The cx / ct loads of the block after the one being converted are always in flight (a cursor over the flat sequence of
-      // (item, layer, 64-column block)): issued one block at a time they cost one DRAM round trip per block, 22 per item.
-      int c_item = first, c_l = 0, c_j = 0;
-      float4 xn[8], tn;
-      const int c4 = (lane & 15) * 4;
-      auto issue = [&]() {
-        if (c_item >= nitems) return;
-        const int ctile = c_item / P.nsteps, tl = c_item - ctile * P.nsteps;
-        const int irev = P.T - 1 - (P.s0 + tl);
-        const int col = P.coff[c_l] + 64 * c_j + c4;
-        tn = __ldg(reinterpret_cast<const float4*>(P.ct + (size_t)irev * P.csum + col));
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long bb = (long long)ctile * 128 + ew * 16 + 2 * u + (lane >> 4);
-          xn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bb < P.B)   // read once per step: keep it out of L1
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(xn[u].x), "=f"(xn[u].y), "=f"(xn[u].z), "=f"(xn[u].w) : "l"(P.cx + bb * P.csum + col));
-        }
-      };
-      auto produce = [&](int l, uint32_t g) {
-        const int nb = P.dout[l] >> 6;
-        for (int j = 0; j < nb; ++j) {
-          float4 x4[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) x4[u] = xn[u];
-          const float4 t4 = tn;
-          if (++c_j == (P.dout[c_l] >> 6)) { c_j = 0; if (++c_l == DEN_LAYERS) { c_l = 0; c_item += stride; } }
-          issue();
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int R = ew * 16 + 2 * u + (lane >> 4);
-            const float a0 = x4[u].x + t4.x, a1 = x4[u].y + t4.y, a2 = x4[u].z + t4.z, a3 = x4[u].w + t4.w;
-            const float s0 = __fdividef(a0, 1.f + __expf(-a0)), s1 = __fdividef(a1, 1.f + __expf(-a1));
-            const float s2 = __fdividef(a2, 1.f + __expf(-a2)), s3 = __fdividef(a3, 1.f + __expf(-a3));
-            const uint32_t dst = blocks + sq_chunk((int)(4u * (g & 1u)) + j, R, c4) + (uint32_t)((c4 & 4) << 1);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack2(fp16, s0, s1)), "r"(pack2(fp16, s2, s3)) : "memory");
-          }
-        }
-        signal(bar_cready(g & 1u), false);
-      };
-      issue();
-      if (first < nitems) produce(0, 0u);
+      // (the ctx operand tiles are formed by the producer warps above; these warps turn accumulators into gate words)
       for (int item = first; item < nitems; item += stride) {
         // chain tile major: the steps of one chain tile run at about the same time on neighbouring CTAs and share its cx rows in L2
         const int ctile = item / P.nsteps, tl = item - ctile * P.nsteps;
         uint4* Gt = P.G + ((size_t)tl * tiles_b + ctile) * (size_t)(P.csum >> 2) * 128 + r;
         int ti = 0;
-        for (int l = 0; l < DEN_LAYERS; ++l, ++lcnt) {
-          // the next layer's operand (possibly the next item's first) is formed while this layer's MMAs run
-          if (l + 1 < DEN_LAYERS) produce(l + 1, lcnt + 1u);
-          else if (item + stride < nitems) produce(0, lcnt + 1u);
+        for (int l = 0; l < DEN_LAYERS; ++l) {
           const int ntl = P.dout[l] >> 7;
           for (int n = 0; n < ntl; ++n, ++ti, ++cnt) {
             const SqTile& T = P.tile[ti];
@@ -519,9 +523,10 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
             const uint32_t t_acc = t_lane + as * 256u;
             mbar_wait_relaxed(bar_accfull(as), (cnt >> 1) & 1u);
             tc_fence_after();
-            const float* bm = sbias + T.goff + half * 64;   // same address in every lane: shared-memory broadcasts
-            const float* bs = bm + P.csum;
-            const float* bg = bs + P.csum;
+            // (same address in every lane; the cx stream bypasses L1, so these 17 KB of biases stay in it)
+            const float* bm = P.bias3[l] + T.ocol0 + half * 64;
+            const float* bs = bm + P.dout[l];
+            const float* bg = bs + P.dout[l];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t vg[16], vh[16];
@@ -531,9 +536,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) den_seq_kernel(const __grid_con
               uint32_t w[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 g4 = *(reinterpret_cast<const float4*>(bg + c * 16) + i4);
-                const float4 s4 = *(reinterpret_cast<const float4*>(bs + c * 16) + i4);
-                const float4 m4 = *(reinterpret_cast<const float4*>(bm + c * 16) + i4);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(bg + c * 16) + i4);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(bs + c * 16) + i4);
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(bm + c * 16) + i4);
                 const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -861,13 +866,15 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     Gp.ntiles = n;
   }
 
-  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_STEP * SQ_WSTAGE + 8 * (2 * SQ_STAGES_STEP + 11) + 16 + 1024;
-  const size_t smem_g = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_GATE * SQ_WSTAGE + 3 * SQ_MAXCSUM * 4 + 8 * (2 * SQ_STAGES_GATE + 11) + 16 + 1024;
+  const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_STEP * SQ_WSTAGE + 8 * (2 * SQ_STAGES_STEP + 13) + 16 + 1024;
+  const size_t smem_g = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_GATE * SQ_WSTAGE + 8 * (2 * SQ_STAGES_GATE + 13) + 16 + 1024;
   int dev = 0, sms = 148;
   DAMC_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  DAMC_CUDA(cudaFuncSetAttribute(den_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DAMC_CUDA(cudaFuncSetAttribute(den_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  auto* const step_kernel = fp16 ? den_seq_kernel<0, true> : den_seq_kernel<0, false>;
+  auto* const gate_kernel = fp16 ? den_seq_kernel<1, true> : den_seq_kernel<1, false>;
+  DAMC_CUDA(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DAMC_CUDA(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   static unsigned long long* tlog = nullptr;
   const bool dbg = getenv("DAMC_SQ_DBG") != nullptr;
   if (dbg && !tlog) { cudaMalloc(&tlog, 128 * 8); }
@@ -888,10 +895,10 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
       count_launch();
     }
     profile_mark(s, true);
-    den_seq_kernel<1><<<std::min(items, sms), SQ_THREADS, smem_g, s>>>(Gp);
+    gate_kernel<<<std::min(items, sms), SQ_THREADS_GATE, smem_g, s>>>(Gp);
     profile_mark(s, false);
     profile_mark(s, true);
-    den_seq_kernel<0><<<Bpad / 128, SQ_THREADS, smem, s>>>(S);
+    step_kernel<<<Bpad / 128, SQ_THREADS, smem, s>>>(S);
     profile_mark(s, false);
     count_launch(2);
   }

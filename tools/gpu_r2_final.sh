@@ -22,4 +22,10 @@ tail -1 gpurun_out/z_configs_bf16.log
 PREC=tf32 timeout 900 python tools/bench_configs.py svhn cifar10 celebaHQ > gpurun_out/z_configs_tf32.log 2>&1
 tail -1 gpurun_out/z_configs_tf32.log
 timeout 600 python tools/bench_secondary.py > gpurun_out/z_secondary.log 2>&1
+timeout 600 python tools/bench_denoiser_seq.py > gpurun_out/z_denoiser_hoisted.json 2> gpurun_out/z_denoiser_hoisted.err
+tail -3 gpurun_out/z_denoiser_hoisted.json
+for b in 128 16384; do
+  timeout 600 ncu --metrics $M --clock-control none -k regex:den_seq --csv --log-file gpurun_out/z_launches_denoiser_hoisted_B$b.csv python tools/profile_denseq.py $b > /dev/null 2>&1
+  echo "ncu denoiser $b exit $?"
+done
 tail -3 gpurun_out/z_secondary.log
