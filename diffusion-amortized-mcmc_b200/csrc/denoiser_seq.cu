@@ -29,12 +29,14 @@
 
 namespace damc {
 
-constexpr int SQ_THREADS = 320;        // warp 0: TMA, warp 1: MMA issuer + TMEM, warps 2-9: workers (two per TMEM lane quarter)
+constexpr int SQ_STEP_NWQ = 2;         // step pass: worker warps per TMEM lane quarter (each thread: one chain row, 128 / NWQ features of a tile)
+constexpr int SQ_THREADS = 64 + 128 * SQ_STEP_NWQ;   // warp 0: TMA, warp 1: MMA issuer + TMEM, then the workers
 constexpr int SQ_GATE_PW = 8;          // gate pass: producer warps (warps 10 ...) that form the ctx operand tiles, 128 / SQ_GATE_PW chain rows each
-constexpr int SQ_THREADS_GATE = 320 + 32 * SQ_GATE_PW;
+constexpr int SQ_THREADS_GATE = 320 + 32 * SQ_GATE_PW;   // warps 2-9: epilogue (two per lane quarter), then the producers
 constexpr int SQ_BLK = 128 * 128;      // one K-major k-block of a 128-row operand tile (64 columns x 16 bit): 16 KB
 constexpr int SQ_NBLK = 8;             // X = blocks 0-3, Y = blocks 4-7
 constexpr int SQ_WSTAGE = 256 * 128;   // one weight k-block: 256 rows x 128 B
+constexpr int SQ_WBOX = 64;          // weight rows per TMA request
 constexpr int SQ_STAGES_STEP = 3;   // step pass: the weight stream feeds the chain of dependent MMAs
 constexpr int SQ_STAGES_GATE = 3;   // (two stages leave the gate pass bound by the ~2 us a 256-row weight box takes to arrive)
 constexpr int SQ_MAXCSUM = 65535;   // tile offsets are 16-bit
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
   uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t blocks = base, ring = base + (uint32_t)SQ_NBLK * SQ_BLK;
   constexpr int SQ_STAGES = MODE == 0 ? SQ_STAGES_STEP : SQ_STAGES_GATE;
+  constexpr int NWQ = MODE == 0 ? SQ_STEP_NWQ : 2, NWORK = 4 * NWQ;   // worker warps per lane quarter / in all
+  constexpr int FPW = 128 / NWQ, NCH = FPW / 16;                      // features of a tile per worker thread, in 16-feature chunks
   const uint32_t off_bars = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
   const uint32_t bars = base + off_bars;
   auto bar_wfull = [&](int s) { return bars + 8u * s; };
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     if (MODE == 0) { prefetch_tmap(&P.tmSkip[0]); prefetch_tmap(&P.tmSkip[1]); }
     for (int s = 0; s < SQ_STAGES; ++s) { mbar_init(bar_wfull(s), 1); mbar_init(bar_wempty(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), 8); mbar_init(bar_hready(s), 8); mbar_init(bar_cready(s), SQ_GATE_PW);
+      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), NWORK); mbar_init(bar_hready(s), NWORK); mbar_init(bar_cready(s), SQ_GATE_PW);
       mbar_init(bar_cfree(s), 1);
     }
     mbar_init(bar_stg, 1);
@@ -191,9 +195,11 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             const int nsub = min(per, T.nkb - kb);
             mbar_wait(bar_wempty(stage), phase ^ 1u);
             mbar_expect_tx(bar_wfull(stage), (uint32_t)nsub * T.wrows * 128u);
+            // SQ_WBOX-row boxes: a stage arrives as several concurrent requests instead of one 256-row box walked row by row
             for (int j = 0; j < nsub; ++j)
-              tma_load_2d(ring + (uint32_t)stage * SQ_WSTAGE + (uint32_t)j * T.wrows * 128u, &P.tmW[T.wmap], bar_wfull(stage),
-                          T.k[kb + j].wcol, T.wrow0);
+              for (int rb = 0; rb < T.wrows; rb += SQ_WBOX)
+                tma_load_2d(ring + (uint32_t)stage * SQ_WSTAGE + (uint32_t)(j * T.wrows + rb) * 128u, &P.tmW[T.wmap], bar_wfull(stage),
+                            T.k[kb + j].wcol, T.wrow0 + rb);
             if (kb == 0 && P.tlog != nullptr && blockIdx.x == 0 && item == first + stride) P.tlog[10 * ti + 8] = sq_now();
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -261,13 +267,13 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
           ++cnt;
         }
     }
-  } else if (MODE == 1 && warp >= 10) {
+  } else if (MODE == 1 && warp >= 2 + NWORK) {
     // ===================== gate pass, 4 producer warps: ctx activations c = SiLU(cx[b] + ct[t]) of global layer g (item, layer) ->
     // c buffer g & 1 (blocks 4 (g & 1) ...).  A warp owns 32 chain rows; 16 lanes cover the 64 columns of a block row (float4
     // each), two rows per instruction, 16 rows per pass.  The cx / ct loads of the pass after the one being converted are always
     // in flight (a cursor over the flat sequence of (item, layer, 64-column block, half)): issued one pass at a time they would
     // cost a DRAM round trip per pass.
-    const int pw = warp - 10;
+    const int pw = warp - 2 - NWORK;
     constexpr bool fp16 = FP16;
     constexpr int PROWS = 128 / SQ_GATE_PW, PH = PROWS / 16;   // rows per producer warp, 16-row passes per block
     int c_item = first, c_l = 0, c_j = 0, c_h = 0;
@@ -318,7 +324,8 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
       }
   } else {
     // ===================== 8 worker warps: two per TMEM lane quarter; a thread owns one chain row and half of a tile's features ====
-    const int ew = warp - 2, q = warp & 3, half = ew >> 2, r = q * 32 + lane;
+    const int ew = warp - 2, q = warp & 3, sub = ew >> 2, r = q * 32 + lane;
+    constexpr int RW = 128 / NWORK;   // rows per warp in the row-major passes
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr bool fp16 = FP16;
     // this warp's part of an operand tile is written (generic proxy): hand it to the async proxy.  all_spaces: also the skip rows
@@ -337,16 +344,16 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
       {
         const int c4 = lane * 4;
 #pragma unroll 1
-        for (int r0 = 0; r0 < 16; r0 += 4) {
+        for (int r0 = 0; r0 < RW; r0 += 4) {
           float4 zq[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const long long bb = (long long)blockIdx.x * 128 + ew * 16 + r0 + u;
+            const long long bb = (long long)blockIdx.x * 128 + ew * RW + r0 + u;
             zq[u] = bb < P.B ? *reinterpret_cast<const float4*>(P.z + bb * P.nz + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int R = ew * 16 + r0 + u;
+            const int R = ew * RW + r0 + u;
             const float v[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
             __half h[4], l[4];
 #pragma unroll
@@ -389,12 +396,13 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
           if (T.kind == SQ_EMB) {
             mbar_wait(bar_accfull(as), (cnt >> 1) & 1u);
             tc_fence_after();
-            // phases of this row's 32 frequencies [half*32, +32): sin -> X0, cos -> X1 (diffusion_net.py:497-499)
+            // phases of this row's 64 / NWQ frequencies: sin -> X0, cos -> X1 (diffusion_net.py:497-499)
+            constexpr int PE = 64 / NWQ;
             uint32_t v[32];
-            tmem_ld32(t_acc + (uint32_t)(half * 32), v);
+            if (PE == 32) tmem_ld32(t_acc + (uint32_t)(sub * PE), v); else tmem_ld16(t_acc + (uint32_t)(sub * PE), v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PE / 8; ++j) {
               uint32_t ws[4], wc[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -405,24 +413,24 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
                 ws[e] = pack2(fp16, s0, s1);
                 wc[e] = pack2(fp16, c0, c1);
               }
-              const int col = half * 32 + j * 8;
+              const int col = sub * PE + j * 8;
               sq_st16(blocks + sq_chunk(0, r, col), ws[0], ws[1], ws[2], ws[3]);
               sq_st16(blocks + sq_chunk(1, r, col), wc[0], wc[1], wc[2], wc[3]);
             }
           } else {
             // the gate / hyper-bias words of this row's 64 features of the tile: requested before the accumulator is waited for
-            uint4 g[16];
-            const uint4* gp = Gt + (size_t)((T.goff >> 2) + half * 16) * 128;
+            uint4 g[FPW / 4];
+            const uint4* gp = Gt + (size_t)((T.goff >> 2) + sub * (FPW / 4)) * 128;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) g[i] = __ldg(gp + i * 128);
+            for (int i = 0; i < FPW / 4; ++i) g[i] = __ldg(gp + i * 128);
             // last layer: this row's z / noise quads, one 16-feature chunk at a time (row-strided 16-byte reads: L2 round trips that
             // must not sit between the accumulator and the update)
             float4 zq[2][4], nq[2][4];
             auto ld_zn = [&](int c, float4 (&zz)[4], float4 (&nn)[4]) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                zz[j] = zt_[(half * 16 + c * 4 + j) * 128];
-                nn[j] = nt_ ? __ldg(nt_ + (half * 16 + c * 4 + j) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                zz[j] = zt_[(sub * (FPW / 4) + c * 4 + j) * 128];
+                nn[j] = nt_ ? __ldg(nt_ + (sub * (FPW / 4) + c * 4 + j) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
             };
             if (T.kind == SQ_FINAL) ld_zn(0, zq[0], nq[0]);
@@ -434,11 +442,11 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             const bool fin = T.kind == SQ_FINAL;
             const bool noisy = fin && !d.last && d.c_std != 0.f && nt_ != nullptr;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NCH; ++c) {
               uint32_t vm[16], vs[16];
-              tmem_ld16(t_acc + (uint32_t)(half * 64 + c * 16), vm);
-              tmem_ld16(t_acc + 128u + (uint32_t)(half * 64 + c * 16), vs);
-              if (fin && c < 3) ld_zn(c + 1, zq[(c + 1) & 1], nq[(c + 1) & 1]);   // the next chunk's z / noise quads: a chunk ahead
+              tmem_ld16(t_acc + (uint32_t)(sub * FPW + c * 16), vm);
+              tmem_ld16(t_acc + 128u + (uint32_t)(sub * FPW + c * 16), vs);
+              if (fin && c < NCH - 1) ld_zn(c + 1, zq[(c + 1) & 1], nq[(c + 1) & 1]);   // the next chunk's z / noise quads: a chunk ahead
               tmem_ld_wait();
               float o[16];
 #pragma unroll
@@ -452,7 +460,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
                   o[i] = fmaf(__uint_as_float(vm[i]), sh.x, __uint_as_float(vs[i]) + sh.y);
                 }
               }
-              const int f = half * 64 + c * 16;   // feature inside the tile
+              const int f = sub * FPW + c * 16;   // feature inside the tile
               if (fin) {
                 // eps = z + out, reverse update of z; the new z also leaves as the fp16 split (zh -> X2,X3 ; zl -> Y0,Y1) for the
                 // next step's embedding GEMM (and as bf16 -> Y2,Y3, the first layer's z operand, in bf16 mode)
@@ -524,14 +532,14 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             mbar_wait_relaxed(bar_accfull(as), (cnt >> 1) & 1u);
             tc_fence_after();
             // (same address in every lane; the cx stream bypasses L1, so these 17 KB of biases stay in it)
-            const float* bm = P.bias3[l] + T.ocol0 + half * 64;
+            const float* bm = P.bias3[l] + T.ocol0 + sub * FPW;
             const float* bs = bm + P.dout[l];
             const float* bg = bs + P.dout[l];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t vg[16], vh[16];
-              tmem_ld16(t_acc + (uint32_t)(half * 64 + c * 16), vg);
-              tmem_ld16(t_acc + 128u + (uint32_t)(half * 64 + c * 16), vh);
+              tmem_ld16(t_acc + (uint32_t)(sub * FPW + c * 16), vg);
+              tmem_ld16(t_acc + 128u + (uint32_t)(sub * FPW + c * 16), vh);
               tmem_ld_wait();
               uint32_t w[16];
 #pragma unroll
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
                   w[i] = pack_f16x2(sig, fmaf(mm[e], sig, __uint_as_float(vh[i]) + ss[e]));
                 }
               }
-              uint4* gp = Gt + (size_t)((T.goff >> 2) + half * 16 + c * 4) * 128;
+              uint4* gp = Gt + (size_t)((T.goff >> 2) + sub * (FPW / 4) + c * 4) * 128;
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) gp[i4 * 128] = make_uint4(w[4 * i4], w[4 * i4 + 1], w[4 * i4 + 2], w[4 * i4 + 3]);
             }
@@ -708,8 +716,8 @@ static int den_seq_ensure(const DenPack* d, int precision, cudaStream_t s) {
   for (int i = 0; i < DEN_LAYERS && r == DAMC_OK; ++i) {
     p->Wms[i] = q; q += align_up(4 * (size_t)d->dout[i] * d->din[i], 256);
     p->Wgh[i] = q; q += align_up(4 * (size_t)d->dout[i] * d->dout[i], 256);
-    r = tc_encode_2d(&p->tmMs[i], fp16, p->Wms[i], d->din[i], 2 * d->dout[i], 256);
-    if (r == DAMC_OK) r = tc_encode_2d(&p->tmGh[i], fp16, p->Wgh[i], d->dout[i], 2 * d->dout[i], 256);
+    r = tc_encode_2d(&p->tmMs[i], fp16, p->Wms[i], d->din[i], 2 * d->dout[i], SQ_WBOX);
+    if (r == DAMC_OK) r = tc_encode_2d(&p->tmGh[i], fp16, p->Wgh[i], d->dout[i], 2 * d->dout[i], SQ_WBOX);
   }
   p->Wemb = (__half*)q;
   if (r == DAMC_OK) r = tc_encode_2d(&p->tmEmb, 1, p->Wemb, 3 * d->nz, d->nz / 2, d->nz / 2);
@@ -877,8 +885,8 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
   DAMC_CUDA(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   static unsigned long long* tlog = nullptr;
   const bool dbg = getenv("DAMC_SQ_DBG") != nullptr;
-  if (dbg && !tlog) { cudaMalloc(&tlog, 128 * 8); }
-  if (dbg) cudaMemsetAsync(tlog, 0, 128 * 8, s);
+  if (dbg && !tlog) { cudaMalloc(&tlog, 256 * 8); }
+  if (dbg) cudaMemsetAsync(tlog, 0, 256 * 8, s);
   S.tlog = dbg ? tlog : nullptr;
   const int win = den_seq_window(B, T, d->csum);
   for (int s0 = 0; s0 < nsteps; s0 += win) {
@@ -904,7 +912,7 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
   }
   DAMC_CUDA(cudaGetLastError());
   if (dbg) {   // experiment mode: stamps of CTA 0's second step, ns relative to the step's first stamp
-    unsigned long long h[128];
+    unsigned long long h[256];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, tlog, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = (long long)h[0];
