@@ -107,6 +107,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void sq_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// exp2 without the denormal-range fix-up __expf carries (3 of its 5 instructions): an argument below -126 flushes to 0, which is the
+// right limit for 1 / (1 + e^-a); the gate pass evaluates 2 816 of these per chain and step and is SFU / issue bound
+__device__ __forceinline__ float sq_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sq_silu_fast(float a) { return __fdividef(a, 1.f + sq_ex2(-1.4426950408889634f * a)); }
 __device__ __forceinline__ void sq_st16(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -312,8 +320,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             for (int u = 0; u < 8; ++u) {
               const int R = pw * PROWS + h * 16 + 2 * u + (lane >> 4);
               const float a0 = x4[u].x + t4.x, a1 = x4[u].y + t4.y, a2 = x4[u].z + t4.z, a3 = x4[u].w + t4.w;
-              const float s0 = __fdividef(a0, 1.f + __expf(-a0)), s1 = __fdividef(a1, 1.f + __expf(-a1));
-              const float s2 = __fdividef(a2, 1.f + __expf(-a2)), s3 = __fdividef(a3, 1.f + __expf(-a3));
+              const float s0 = sq_silu_fast(a0), s1 = sq_silu_fast(a1), s2 = sq_silu_fast(a2), s3 = sq_silu_fast(a3);
               const uint32_t dst = blocks + sq_chunk((int)(4u * (g & 1u)) + j, R, c4) + (uint32_t)((c4 & 4) << 1);
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack2(fp16, s0, s1)), "r"(pack2(fp16, s2, s3)) : "memory");
             }
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
                 for (int e = 0; e < 4; ++e) {
                   const int i = i4 * 4 + e;
                   const float gate = __uint_as_float(vg[i]) + gg[e];
-                  const float sig = __fdividef(1.f, 1.f + __expf(-gate));
+                  const float sig = __fdividef(1.f, 1.f + sq_ex2(-1.4426950408889634f * gate));
                   // everything of out = (main + b) sig + hb + skip + bs that does not depend on h:  (sig, hb + bs + b sig)
                   w[i] = pack_f16x2(sig, fmaf(mm[e], sig, __uint_as_float(vh[i]) + ss[e]));
                 }
@@ -887,7 +894,9 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
   const bool dbg = getenv("DAMC_SQ_DBG") != nullptr;
   if (dbg && !tlog) { cudaMalloc(&tlog, 256 * 8); }
   if (dbg) cudaMemsetAsync(tlog, 0, 256 * 8, s);
-  S.tlog = dbg ? tlog : nullptr;
+  const bool dbg_gate = dbg && getenv("DAMC_SQ_DBG")[0] == '2';   // 2: stamps of the gate pass's MMA thread instead
+  S.tlog = (dbg && !dbg_gate) ? tlog : nullptr;
+  Gp.tlog = dbg_gate ? tlog : nullptr;
   const int win = den_seq_window(B, T, d->csum);
   for (int s0 = 0; s0 < nsteps; s0 += win) {
     const int ns = std::min(win, nsteps - s0);
@@ -916,6 +925,14 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     cudaStreamSynchronize(s);
     cudaMemcpy(h, tlog, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = (long long)h[0];
+    if (dbg_gate) {
+      for (int ti = 0; ti < Gp.ntiles; ++ti) {
+        const unsigned long long* e = h + 10 * ti;
+        fprintf(stderr, "[sq gate] tile %2d L%d: tma-kb0 %6lld | mma-start %6lld acc-free %6lld ctx-ready+w-wait %6lld w-full %6lld issued %6lld\n", ti,
+                Gp.tile[ti].layer, (long long)e[8] - t0, (long long)e[0] - t0, (long long)e[1] - t0, (long long)e[2] - t0, (long long)e[3] - t0, (long long)e[4] - t0);
+      }
+      return DAMC_OK;
+    }
     for (int ti = 0; ti < S.ntiles; ++ti) {
       const unsigned long long* e = h + 10 * ti;
       fprintf(stderr, "[sq] tile %2d kind %d L%d: tma-kb0 %6lld | mma-start %6lld acc-free %6lld w-wait %6lld w-full %6lld issued %6lld | epi: wait-start %6lld acc-full %6lld done %6lld last-warp %6lld\n",

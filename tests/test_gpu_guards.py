@@ -69,9 +69,14 @@ def test_posterior_and_generator_stay_inside_their_buffers(dataset, nz, ngf, nc,
 
 @pytest.mark.parametrize("B", [1, 130, 2100])
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
-def test_denoiser_and_encoder_stay_inside_their_buffers(B, prec, guarded):
+@pytest.mark.parametrize("schedule", ["hoisted", "round1"])
+def test_denoiser_and_encoder_stay_inside_their_buffers(B, prec, schedule, guarded, monkeypatch):
     from damc_b200 import MCMC, diffusion_net as dn
     dev, check = guarded
+    if schedule == "round1":   # cluster kernel / per-layer launches + graph instead of the hoisted-context schedule (16-bit modes)
+        if prec == "fp32":
+            pytest.skip("the fp32 kernel has one schedule")
+        monkeypatch.setenv("DAMC_DEN_SEQ", "0")
     T = 6
     Q = dn._netQ_U(nc=3, nz=128, nxemb=256, ntemb=128, nif=64, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
                    logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10")

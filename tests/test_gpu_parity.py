@@ -428,13 +428,16 @@ def test_damc_tensor_core_matches_fp32_kernel_on_ragged_batches(B, dev):
         assert torch.equal(one[0], outs["fp16"][0])
 
 
-def test_damc_graph_replay_matches_direct_launches(dev):
+def test_damc_graph_replay_matches_direct_launches(dev, monkeypatch):
     """The tcgen05 DAMC loop is captured into a CUDA graph the second time a configuration is seen and replayed afterwards
     (z staged through the workspace, Philox seed read from device memory).  Direct launches (call 1), the capturing call
     (2) and replays (3+) must agree bit for bit; a new seed on a replay must give new noise, equal to a direct run's."""
     from damc_b200 import MCMC, diffusion_net as dn
     # B > 8 x 128: the one-launch cluster kernel does not take the batch, so the per-layer launches -- the path that is
     # captured into a graph (denoiser_tc.cu) -- run.  (Up to 1 024 chains den_cluster_run returns before the graph code.)
+    # DAMC_DEN_SEQ=0 (read per call): the default hoisted-context schedule (denoiser_seq.cu, tests/test_gpu_denoiser_seq.py) has no
+    # launch sequence to capture.
+    monkeypatch.setenv("DAMC_DEN_SEQ", "0")
     T, nz, B = 16, 128, 1100
     Q = dn._netQ_U(nc=3, nz=nz, nxemb=1024, ntemb=128, nif=64, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
                    logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10")

@@ -11,6 +11,6 @@ xemb = torch.randn(B, 1024, device=dev) * 0.5
 zT = torch.randn(B, 128)
 for i in range(3):
     if i == 2:
-        os.environ["DAMC_SQ_DBG"] = "1"
+        os.environ["DAMC_SQ_DBG"] = os.environ.get("SQ_DBG_MODE", "1")
     MCMC.damc_sample(Q, xemb=xemb, z_init=zT, seed=5, precision="fp16")
     torch.cuda.synchronize()
