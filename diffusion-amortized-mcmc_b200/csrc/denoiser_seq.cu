@@ -36,6 +36,7 @@ constexpr int SQ_THREADS_GATE = 320 + 32 * SQ_GATE_PW;   // warps 2-9: epilogue 
 constexpr int SQ_BLK = 128 * 128;      // one K-major k-block of a 128-row operand tile (64 columns x 16 bit): 16 KB
 constexpr int SQ_NBLK = 8;             // X = blocks 0-3, Y = blocks 4-7
 constexpr int SQ_WSTAGE = 256 * 128;   // one weight k-block: 256 rows x 128 B
+constexpr int SQ_PF_AHEAD = 5;       // tiles between the L2 prefetch of a tile's gate words and the tile (the producer itself runs up to 3 k-blocks ahead)
 constexpr int SQ_WBOX = 64;          // weight rows per TMA request
 constexpr int SQ_STAGES_STEP = 3;   // step pass: the weight stream feeds the chain of dependent MMAs
 constexpr int SQ_STAGES_GATE = 3;   // (two stages leave the gate pass bound by the ~2 us a 256-row weight box takes to arrive)
@@ -179,12 +180,12 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
         if (pitem >= nitems || P.tile[pt].kind == SQ_EMB) return;
         sq_prefetch_l2(P.G + (((size_t)pitem * tiles_b + blockIdx.x) * (size_t)(P.csum >> 2) + (P.tile[pt].goff >> 2)) * 128, 128u * 128u * 4u);
       };
-      if (MODE == 0) { prefetch_g(0, 1); prefetch_g(0, 2); }
+      if (MODE == 0) for (int pt = 1; pt < SQ_PF_AHEAD; ++pt) prefetch_g(0, pt);
       for (int item = first; item < nitems; item += stride)
         for (int ti = 0; ti < P.ntiles; ++ti) {
           const SqTile& T = P.tile[ti];
-          if (MODE == 0) {   // three tiles ahead; the step's normals half a step ahead
-            const int pt = ti + 3;
+          if (MODE == 0) {   // SQ_PF_AHEAD tiles ahead; the step's normals half a step ahead
+            const int pt = ti + SQ_PF_AHEAD;
             if (pt < P.ntiles) prefetch_g(item, pt); else prefetch_g(item + 1, pt - P.ntiles);
             if (ti == 4 && P.noiseT)
               sq_prefetch_l2(P.noiseT + ((size_t)item * tiles_b + blockIdx.x) * (size_t)(P.nz >> 2) * 128, 128u * (uint32_t)P.nz * 4u);
@@ -590,15 +591,16 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
 __global__ void __launch_bounds__(256) den_seq_noise_kernel(float4* __restrict__ out, const float* __restrict__ src, int B, int Bpad,
                                                             int nz, int T, int s0, int ns, unsigned long long seed,
                                                             unsigned long long chain0) {
-  const int q4 = nz >> 2, tiles_b = Bpad >> 7;
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= (long long)ns * Bpad * q4) return;
-  const int r = (int)(i & 127);
-  const long long t1 = i >> 7;
-  const int quad = (int)(t1 % q4);
-  const long long t2 = t1 / q4;
-  const int ctile = (int)(t2 % tiles_b), st = (int)(t2 / tiles_b);
+  // grid (Bpad * nz / 4 / 256, ns): 32-bit index arithmetic (64-bit divisions cost more than the Philox rounds)
+  const uint32_t q4 = (uint32_t)nz >> 2;
+  const uint32_t j = blockIdx.x * 256u + threadIdx.x;   // (chain tile, quad, row) of step blockIdx.y
+  if (j >= (uint32_t)Bpad * q4) return;
+  const int r = (int)(j & 127u);
+  const uint32_t t1 = j >> 7;
+  const int ctile = (int)(t1 / q4), quad = (int)(t1 - (uint32_t)ctile * q4), st = (int)blockIdx.y;
+  const size_t i = (size_t)st * Bpad * q4 + j;
   const int b = ctile * 128 + r, sg = s0 + st;
+  (void)ns;
   float n[4] = {0.f, 0.f, 0.f, 0.f};
   if (b < B && sg < T - 1) {   // the last step adds no noise (and injected noise has T - 1 slabs)
     if (src) {
@@ -764,7 +766,7 @@ int den_seq_hoist(const DenPack* d, int precision, const DenWs& w, const float* 
 // steps per window: the gate pass writes G for this many steps, then the step pass consumes them
 int den_seq_window(int B, int T, int csum) {
   const size_t per_step = (size_t)align_up(B, 128) * csum * 4;
-  const size_t budget = (size_t)1 << 30;
+  const size_t budget = (size_t)4 << 30;   // of gate words (fewer, longer launches: the gate pass wastes its last partial round of items)
   const char* e = getenv("DAMC_DEN_SEQ_WINDOW");   // test switch: force short windows (read per call, by den_ws and the run alike)
   if (e && atoi(e) > 0) return std::min(T, atoi(e));
   return (int)std::max<size_t>(1, std::min<size_t>((size_t)T, budget / per_step));
@@ -906,8 +908,8 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
     for (int k = s0; k < s0 + ns; ++k) noisy = noisy || (host_coef[8 * (size_t)k + 4] != 0.f && host_coef[8 * (size_t)k + 5] == 0.f);
     S.noiseT = nullptr;
     if (noisy && (noise != nullptr || use_philox)) {
-      const long long nq = (long long)ns * Bpad * (d->nz / 4);
-      den_seq_noise_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(reinterpret_cast<float4*>(w.nbuf), noise, B, Bpad, d->nz, T, s0, ns, seed, chain0);
+      const long long nq = (long long)Bpad * (d->nz / 4);
+      den_seq_noise_kernel<<<dim3((unsigned)((nq + 255) / 256), (unsigned)ns), 256, 0, s>>>(reinterpret_cast<float4*>(w.nbuf), noise, B, Bpad, d->nz, T, s0, ns, seed, chain0);
       S.noiseT = reinterpret_cast<const float4*>(w.nbuf);
       count_launch();
     }

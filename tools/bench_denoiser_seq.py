@@ -35,7 +35,7 @@ Q = dn._netQ_U(nc=3, nz=128, nxemb=1024, ntemb=128, nif=64, diffusion_residual=T
 out = {}
 for B in (128, 1024, 4096, 16384):
     xemb = torch.randn(B, 1024, device=dev) * 0.5
-    zT = torch.randn(B, 128)
+    zT = torch.randn(B, 128, device=dev)   # (a host z_T would put a pageable 8 MB copy per call into the timing at 16 384 chains)
     for prec in ("fp16", "bf16"):
         for seq, name in (("1", "hoisted"), ("0", "other")):
             os.environ["DAMC_DEN_SEQ"] = seq

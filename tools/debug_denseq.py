@@ -58,7 +58,7 @@ if what in ("all", "time"):
                    logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10").to(dev).eval()
     for B in (128, 1024, 4096, 16384):
         xemb = torch.randn(B, 1024, device=dev) * 0.5
-        zT = torch.randn(B, 128)
+        zT = torch.randn(B, 128, device=dev)
         line = f"B={B} T=100 (xemb given):"
         for seq in ("1", "0"):
             os.environ["DAMC_DEN_SEQ"] = seq

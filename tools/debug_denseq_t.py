@@ -8,7 +8,7 @@ Q = dn._netQ_U(nc=3, nz=128, nxemb=1024, ntemb=128, nif=64, diffusion_residual=T
                logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10").to(dev).eval()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 xemb = torch.randn(B, 1024, device=dev) * 0.5
-zT = torch.randn(B, 128)
+zT = torch.randn(B, 128, device=dev)
 for i in range(3):
     if i == 2:
         os.environ["DAMC_SQ_DBG"] = os.environ.get("SQ_DBG_MODE", "1")
