@@ -124,16 +124,22 @@ __device__ __forceinline__ uint32_t sq_chunk(int blk, int r, int col) {
   return (uint32_t)blk * SQ_BLK + (uint32_t)r * 128u + (uint32_t)((((col & 63) >> 3) ^ (r & 7)) << 4);
 }
 
-template <int MODE, bool FP16>   // FP16: operand type fp16 (else bf16), a compile-time constant in every conversion
+// FP16: operand type fp16 (else bf16), a compile-time constant in every conversion.  PAIR (gate pass only): two CTAs of a cluster work
+// on two items in lockstep as ONE tcgen05 unit (cta_group::2, M = 256: each CTA's 128 chain rows against weight tiles of which each CTA
+// holds -- and receives from L2 -- only half): the weight ring is 6 stages of 16 KB instead of 3 of 32 KB, and a ring delivers
+// (bytes in flight) / (1.75 us of TMA latency).  The leader CTA's MMA thread issues for the pair; its barriers collect both CTAs' arrivals.
+template <int MODE, bool FP16, bool PAIR>
 __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) den_seq_kernel(const __grid_constant__ SqParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t blocks = base, ring = base + (uint32_t)SQ_NBLK * SQ_BLK;
-  constexpr int SQ_STAGES = MODE == 0 ? SQ_STAGES_STEP : SQ_STAGES_GATE;
+  constexpr int SQ_STAGES = (MODE == 0 ? SQ_STAGES_STEP : SQ_STAGES_GATE) * (PAIR ? 2 : 1);
+  constexpr uint32_t WST = PAIR ? SQ_WSTAGE / 2 : SQ_WSTAGE;   // bytes of a weight stage in this CTA
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int NWQ = MODE == 0 ? SQ_STEP_NWQ : 2, NWORK = 4 * NWQ;   // worker warps per lane quarter / in all
   constexpr int FPW = 128 / NWQ, NCH = FPW / 16;                      // features of a tile per worker thread, in 16-feature chunks
-  const uint32_t off_bars = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * SQ_WSTAGE;
+  const uint32_t off_bars = (uint32_t)SQ_NBLK * SQ_BLK + (uint32_t)SQ_STAGES * WST;
   const uint32_t bars = base + off_bars;
   auto bar_wfull = [&](int s) { return bars + 8u * s; };
   auto bar_wempty = [&](int s) { return bars + 8u * (SQ_STAGES + s); };
@@ -153,7 +159,8 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     if (MODE == 0) { prefetch_tmap(&P.tmSkip[0]); prefetch_tmap(&P.tmSkip[1]); }
     for (int s = 0; s < SQ_STAGES; ++s) { mbar_init(bar_wfull(s), 1); mbar_init(bar_wempty(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), NWORK); mbar_init(bar_hready(s), NWORK); mbar_init(bar_cready(s), SQ_GATE_PW);
+      mbar_init(bar_accfull(s), 1); mbar_init(bar_accempty(s), NWORK * (PAIR ? 2 : 1)); mbar_init(bar_hready(s), NWORK);
+      mbar_init(bar_cready(s), SQ_GATE_PW * (PAIR ? 2 : 1));
       mbar_init(bar_cfree(s), 1);
     }
     mbar_init(bar_stg, 1);
@@ -161,9 +168,10 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     mbar_init(bar_xfree, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -171,6 +179,12 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
   const int tiles_b = P.Bpad >> 7;
   const int nitems = MODE == 0 ? P.nsteps : P.nsteps * tiles_b;
   const int first = MODE == 0 ? 0 : (int)blockIdx.x, stride = MODE == 0 ? 1 : (int)gridDim.x;
+  // iterations of this CTA; a pair runs the same number in both CTAs (the one without an item of its own repeats the last item:
+  // same values to the same addresses)
+  const int niter = PAIR ? (nitems + stride - 1) / stride : (nitems - first + stride - 1) / stride;
+  auto item_of = [&](int it) { return min(first + it * stride, nitems - 1); };
+  // leader-side barriers as cluster addresses (for the non-leader's arrivals)
+  auto lead = [&](uint32_t bar) { return PAIR ? mapa_u32(bar, 0u) : bar; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -181,7 +195,8 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
         sq_prefetch_l2(P.G + (((size_t)pitem * tiles_b + blockIdx.x) * (size_t)(P.csum >> 2) + (P.tile[pt].goff >> 2)) * 128, 128u * 128u * 4u);
       };
       if (MODE == 0) for (int pt = 1; pt < SQ_PF_AHEAD; ++pt) prefetch_g(0, pt);
-      for (int item = first; item < nitems; item += stride)
+      for (int it = 0; it < niter; ++it) {
+        const int item = item_of(it);
         for (int ti = 0; ti < P.ntiles; ++ti) {
           const SqTile& T = P.tile[ti];
           if (MODE == 0) {   // SQ_PF_AHEAD tiles ahead; the step's normals half a step ahead
@@ -203,33 +218,45 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
           for (int kb = 0; kb < T.nkb; kb += per) {
             const int nsub = min(per, T.nkb - kb);
             mbar_wait(bar_wempty(stage), phase ^ 1u);
-            mbar_expect_tx(bar_wfull(stage), (uint32_t)nsub * T.wrows * 128u);
-            // SQ_WBOX-row boxes: a stage arrives as several concurrent requests instead of one 256-row box walked row by row
-            for (int j = 0; j < nsub; ++j)
-              for (int rb = 0; rb < T.wrows; rb += SQ_WBOX)
-                tma_load_2d(ring + (uint32_t)stage * SQ_WSTAGE + (uint32_t)(j * T.wrows + rb) * 128u, &P.tmW[T.wmap], bar_wfull(stage),
-                            T.k[kb + j].wcol, T.wrow0 + rb);
-            if (kb == 0 && P.tlog != nullptr && blockIdx.x == 0 && item == first + stride) P.tlog[10 * ti + 8] = sq_now();
+            if (PAIR) {
+              // this CTA's half of the tile's weight rows; both CTAs' loads report to the LEADER's full barrier, which expects the
+              // bytes of the whole pair
+              if (cta_rank == 0) mbar_expect_tx(bar_wfull(stage), (uint32_t)T.wrows * 128u);
+              const uint32_t lead_full = mapa_u32(bar_wfull(stage), 0u);
+              const int half_rows = T.wrows >> 1;
+              for (int rb = 0; rb < half_rows; rb += SQ_WBOX)
+                tma_load_2d_2sm(ring + (uint32_t)stage * WST + (uint32_t)rb * 128u, &P.tmW[T.wmap], lead_full, T.k[kb].wcol,
+                                T.wrow0 + (int)cta_rank * half_rows + rb);
+            } else {
+              mbar_expect_tx(bar_wfull(stage), (uint32_t)nsub * T.wrows * 128u);
+              // SQ_WBOX-row boxes: a stage arrives as several concurrent requests instead of one 256-row box walked row by row
+              for (int j = 0; j < nsub; ++j)
+                for (int rb = 0; rb < T.wrows; rb += SQ_WBOX)
+                  tma_load_2d(ring + (uint32_t)stage * WST + (uint32_t)(j * T.wrows + rb) * 128u, &P.tmW[T.wmap], bar_wfull(stage),
+                              T.k[kb + j].wcol, T.wrow0 + rb);
+            }
+            if (kb == 0 && P.tlog != nullptr && blockIdx.x == 0 && it == 1) P.tlog[10 * ti + 8] = sq_now();
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0, hph[2] = {0u, 0u}, stgph = 0u;
       uint32_t cnt = 0, lcnt = 0;
-      for (int item = first; item < nitems; item += stride)
+      for (int it = 0; it < niter; ++it)
         for (int ti = 0; ti < P.ntiles; ++ti) {
           const SqTile& T = P.tile[ti];
           const uint32_t as = cnt & 1u;
-          const bool lg = P.tlog != nullptr && blockIdx.x == 0 && item == first + stride;
+          const bool lg = P.tlog != nullptr && blockIdx.x == 0 && it == 1;
           if (lg) P.tlog[10 * ti + 0] = sq_now();
           mbar_wait(bar_accempty(as), ((cnt >> 1) & 1u) ^ 1u);
           tc_fence_after();
           if (lg) P.tlog[10 * ti + 1] = sq_now();
           const uint32_t d_tmem = tmem_base + as * 256u;
-          const uint32_t idesc = T.kind == SQ_EMB ? P.idesc_e : P.idesc_l;
+          const uint32_t idesc = T.kind == SQ_EMB ? P.idesc_e : (PAIR ? (P.idesc_l & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24) : P.idesc_l);
           const uint32_t cbase = MODE == 1 ? 4u * (lcnt & 1u) : 0u;
           const int per = T.kind == SQ_EMB ? 4 : 1;
           for (int kb = 0; kb < T.nkb; kb += per) {
@@ -254,12 +281,14 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             if (lg && kb == 0) P.tlog[10 * ti + 3] = sq_now();
             for (int j = 0; j < nsub; ++j) {
               const uint64_t adesc = make_sdesc(blocks + (cbase + T.k[kb + j].ablk) * SQ_BLK);
-              const uint64_t bdesc = make_sdesc(ring + (uint32_t)stage * SQ_WSTAGE + (uint32_t)j * T.wrows * 128u);
+              const uint64_t bdesc = make_sdesc(ring + (uint32_t)stage * WST + (uint32_t)j * T.wrows * 128u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (PAIR) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
+              }
             }
-            umma_commit(bar_wempty(stage));
+            if (PAIR) umma_commit_2sm(bar_wempty(stage)); else umma_commit(bar_wempty(stage));
             if (T.xcommit && T.xcommit == kb + nsub) umma_commit(bar_xfree);
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -268,10 +297,12 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             else if (T.rdwait == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (T.fullwait) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           }
-          umma_commit(bar_accfull(as));
+          if (PAIR) umma_commit_2sm(bar_accfull(as)); else umma_commit(bar_accfull(as));
           if (lg) P.tlog[10 * ti + 4] = sq_now();
           if (T.commit_ldone) umma_commit(bar_ldone);
-          if (MODE == 1 && T.layer_last) umma_commit(bar_cfree(lcnt & 1u));   // the ctx buffer of this layer may be rewritten
+          if (MODE == 1 && T.layer_last) {   // the ctx buffer of this layer may be rewritten
+            if (PAIR) umma_commit_2sm(bar_cfree(lcnt & 1u)); else umma_commit(bar_cfree(lcnt & 1u));
+          }
           if (T.layer_last) ++lcnt;
           ++cnt;
         }
@@ -285,11 +316,12 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     const int pw = warp - 2 - NWORK;
     constexpr bool fp16 = FP16;
     constexpr int PROWS = 128 / SQ_GATE_PW, PH = PROWS / 16;   // rows per producer warp, 16-row passes per block
-    int c_item = first, c_l = 0, c_j = 0, c_h = 0;
+    int c_it = 0, c_l = 0, c_j = 0, c_h = 0;
     float4 xn[8], tn;
     const int c4 = (lane & 15) * 4;
     auto issue = [&]() {
-      if (c_item >= nitems) return;
+      if (c_it >= niter) return;
+      const int c_item = item_of(c_it);
       const int ctile = c_item / P.nsteps, tl = c_item - ctile * P.nsteps;
       const int irev = P.T - 1 - (P.s0 + tl);
       const int col = P.coff[c_l] + 64 * c_j + c4;
@@ -305,7 +337,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     };
     issue();
     uint32_t g = 0;
-    for (int item = first; item < nitems; item += stride)
+    for (int it = 0; it < niter; ++it)
       for (int l = 0; l < DEN_LAYERS; ++l, ++g) {
         if (g >= 2) mbar_wait_relaxed(bar_cfree(g & 1u), ((g >> 1) - 1u) & 1u);   // the MMAs of layer g - 2 have read this buffer
         const int nb = P.dout[l] >> 6;
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
 #pragma unroll
             for (int u = 0; u < 8; ++u) x4[u] = xn[u];
             const float4 t4 = tn;
-            if (++c_h == PH) { c_h = 0; if (++c_j == (P.dout[c_l] >> 6)) { c_j = 0; if (++c_l == DEN_LAYERS) { c_l = 0; c_item += stride; } } }
+            if (++c_h == PH) { c_h = 0; if (++c_j == (P.dout[c_l] >> 6)) { c_j = 0; if (++c_l == DEN_LAYERS) { c_l = 0; ++c_it; } } }
             issue();
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -328,7 +360,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
           }
         fence_proxy_async();   // generic-proxy writes of the tile -> the tensor core's reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cready(g & 1u));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead(bar_cready(g & 1u))); else mbar_arrive(bar_cready(g & 1u)); }
       }
   } else {
     // ===================== 8 worker warps: two per TMEM lane quarter; a thread owns one chain row and half of a tile's features ====
@@ -526,7 +558,8 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
     } else {
       // ---------------------------------------------- gate pass ----------------------------------------------------------------
       // (the ctx operand tiles are formed by the producer warps above; these warps turn accumulators into gate words)
-      for (int item = first; item < nitems; item += stride) {
+      for (int it = 0; it < niter; ++it) {
+        const int item = item_of(it);
         // chain tile major: the steps of one chain tile run at about the same time on neighbouring CTAs and share its cx rows in L2
         const int ctile = item / P.nsteps, tl = item - ctile * P.nsteps;
         uint4* Gt = P.G + ((size_t)tl * tiles_b + ctile) * (size_t)(P.csum >> 2) * 128 + r;
@@ -571,7 +604,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty(as));
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead(bar_accempty(as))); else mbar_arrive(bar_accempty(as)); }
           }
         }
       }
@@ -579,9 +612,10 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA may retire while the pair's MMAs / multicast arrives can still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -884,12 +918,15 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
   }
 
   const size_t smem = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_STEP * SQ_WSTAGE + 8 * (2 * SQ_STAGES_STEP + 13) + 16 + 1024;
-  const size_t smem_g = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_GATE * SQ_WSTAGE + 8 * (2 * SQ_STAGES_GATE + 13) + 16 + 1024;
+  const size_t smem_g = (size_t)SQ_NBLK * SQ_BLK + (size_t)SQ_STAGES_GATE * SQ_WSTAGE + 8 * (4 * SQ_STAGES_GATE + 13) + 16 + 1024;
   int dev = 0, sms = 148;
   DAMC_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  auto* const step_kernel = fp16 ? den_seq_kernel<0, true> : den_seq_kernel<0, false>;
-  auto* const gate_kernel = fp16 ? den_seq_kernel<1, true> : den_seq_kernel<1, false>;
+  const char* epair = getenv("DAMC_SQ_PAIR");   // experiment switch: 0 = the gate pass without CTA pairs
+  const bool pair = !(epair && epair[0] == '0') && sms >= 2;
+  auto* const step_kernel = fp16 ? den_seq_kernel<0, true, false> : den_seq_kernel<0, false, false>;
+  auto* const gate_kernel = pair ? (fp16 ? den_seq_kernel<1, true, true> : den_seq_kernel<1, false, true>)
+                                 : (fp16 ? den_seq_kernel<1, true, false> : den_seq_kernel<1, false, false>);
   DAMC_CUDA(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DAMC_CUDA(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   static unsigned long long* tlog = nullptr;
@@ -914,7 +951,19 @@ int den_seq_run(const DenPack* d, int precision, const DenWs& w, float* z, int B
       count_launch();
     }
     profile_mark(s, true);
-    gate_kernel<<<std::min(items, sms), SQ_THREADS_GATE, smem_g, s>>>(Gp);
+    {
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = pair ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)(pair ? std::min((items + 1) & ~1, sms & ~1) : std::min(items, sms)));
+      cfg.blockDim = dim3(SQ_THREADS_GATE);
+      cfg.dynamicSmemBytes = smem_g;
+      cfg.stream = s;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      DAMC_CUDA(cudaLaunchKernelEx(&cfg, gate_kernel, Gp));
+    }
     profile_mark(s, false);
     profile_mark(s, true);
     step_kernel<<<Bpad / 128, SQ_THREADS, smem, s>>>(S);
