@@ -103,6 +103,42 @@ __device__ __forceinline__ unsigned long long sq_now() {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// tcgen05.mma / tcgen05.commit issued by ONE elected lane of a CONVERGED warp.  Inside `if (lane == 0)` the compiler has to wrap
+// every such instruction (uniform-datapath operands) into an elect-and-retry loop and re-materialise its uniform registers; with
+// the whole warp running the loop and the election inside the asm statement, a k-block costs the issuing warp half the instructions
+// -- and that warp's instruction stream, not the tensor pipe, paced the MMA-bound stretches (0.55 us per k-block).
+template <bool PAIR>
+__device__ __forceinline__ void sq_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred pe, pa;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred pe, pa;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void sq_commit(uint32_t bar) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
+}
 // pull a contiguous global range into L2 (no destination in the SM): the epilogues' per-tile streams are requested only a tile's MMA
 // time before they are needed -- less than a DRAM round trip under load
 __device__ __forceinline__ void sq_prefetch_l2(const void* p, uint32_t bytes) {
@@ -242,7 +278,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {   // the WHOLE warp runs this loop (converged): waits by every lane, issue by an elected one (sq_umma)
       int stage = 0;
       uint32_t phase = 0, hph[2] = {0u, 0u}, stgph = 0u;
       uint32_t cnt = 0, lcnt = 0;
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
         for (int ti = 0; ti < P.ntiles; ++ti) {
           const SqTile& T = P.tile[ti];
           const uint32_t as = cnt & 1u;
-          const bool lg = P.tlog != nullptr && blockIdx.x == 0 && it == 1;
+          const bool lg = P.tlog != nullptr && blockIdx.x == 0 && it == 1 && lane == 0;
           if (lg) P.tlog[10 * ti + 0] = sq_now();
           mbar_wait(bar_accempty(as), ((cnt >> 1) & 1u) ^ 1u);
           tc_fence_after();
@@ -269,7 +305,7 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             if (MODE == 0) {
 #pragma unroll
               for (int q = 0; q < 2; ++q)
-                if (T.st[q].kb == kb) {
+                if (T.st[q].kb == kb && lane == 0) {
                   tma_store_2d(&P.tmSkip[T.st[q].sel], blocks + (uint32_t)T.st[q].blk0 * SQ_BLK, T.st[q].col0, (int)blockIdx.x * 128);
                   tma_store_2d(&P.tmSkip[T.st[q].sel], blocks + (uint32_t)(T.st[q].blk0 + 1) * SQ_BLK, T.st[q].col0 + 64, (int)blockIdx.x * 128);
                   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -283,26 +319,23 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
               const uint64_t adesc = make_sdesc(blocks + (cbase + T.k[kb + j].ablk) * SQ_BLK);
               const uint64_t bdesc = make_sdesc(ring + (uint32_t)stage * WST + (uint32_t)j * T.wrows * 128u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (PAIR) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
-                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
-              }
+              for (int k = 0; k < 4; ++k)
+                sq_umma<PAIR>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
             }
-            if (PAIR) umma_commit_2sm(bar_wempty(stage)); else umma_commit(bar_wempty(stage));
-            if (T.xcommit && T.xcommit == kb + nsub) umma_commit(bar_xfree);
+            sq_commit<PAIR>(bar_wempty(stage));
+            if (T.xcommit && T.xcommit == kb + nsub) sq_commit<PAIR>(bar_xfree);
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (MODE == 0) {   // (the stores were issued microseconds ago: these waits do not stall)
+          if (MODE == 0 && lane == 0) {   // (the stores were issued microseconds ago: these waits do not stall)
             if (T.rdwait == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
             else if (T.rdwait == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (T.fullwait) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           }
-          if (PAIR) umma_commit_2sm(bar_accfull(as)); else umma_commit(bar_accfull(as));
+          __syncwarp();   // lane 0's bulk-group waits precede the commit that lets the epilogue overwrite the stored blocks
+          sq_commit<PAIR>(bar_accfull(as));
           if (lg) P.tlog[10 * ti + 4] = sq_now();
-          if (T.commit_ldone) umma_commit(bar_ldone);
-          if (MODE == 1 && T.layer_last) {   // the ctx buffer of this layer may be rewritten
-            if (PAIR) umma_commit_2sm(bar_cfree(lcnt & 1u)); else umma_commit(bar_cfree(lcnt & 1u));
-          }
+          if (T.commit_ldone) sq_commit<PAIR>(bar_ldone);
+          if (MODE == 1 && T.layer_last) sq_commit<PAIR>(bar_cfree(lcnt & 1u));   // the ctx buffer of this layer may be rewritten
           if (T.layer_last) ++lcnt;
           ++cnt;
         }
