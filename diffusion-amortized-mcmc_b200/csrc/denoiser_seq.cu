@@ -36,7 +36,7 @@ constexpr int SQ_THREADS_GATE = 320 + 32 * SQ_GATE_PW;   // warps 2-9: epilogue 
 constexpr int SQ_BLK = 128 * 128;      // one K-major k-block of a 128-row operand tile (64 columns x 16 bit): 16 KB
 constexpr int SQ_NBLK = 8;             // X = blocks 0-3, Y = blocks 4-7
 constexpr int SQ_WSTAGE = 256 * 128;   // one weight k-block: 256 rows x 128 B
-constexpr int SQ_PF_AHEAD = 5;       // tiles between the L2 prefetch of a tile's gate words and the tile (the producer itself runs up to 3 k-blocks ahead)
+constexpr int SQ_PF_AHEAD = 3;       // tiles between the L2 prefetch of a tile's gate words and the tile (the producer itself runs up to 3 k-blocks ahead)
 constexpr int SQ_WBOX = 64;          // weight rows per TMA request
 constexpr int SQ_STAGES_STEP = 3;   // step pass: the weight stream feeds the chain of dependent MMAs
 constexpr int SQ_STAGES_GATE = 3;   // (two stages leave the gate pass bound by the ~2 us a 256-row weight box takes to arrive)

@@ -470,7 +470,13 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The WHOLE warp runs the issue loop (converged: every lane waits on the barriers), one elected lane issues (umma_elect).
+    // DAMC_TC_ISSUE=lane0 at build time keeps the round-1 form (lane 0 alone in the loop) for A/B.
+#ifdef DAMC_TC_ISSUE_LANE0
     if (lane == 0 && cta_rank == 0) {
+#else
+    if (cta_rank == 0) {
+#endif
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -494,6 +500,7 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // +32 bytes (16 bf16 | 8 tf32) along K inside the 128-byte swizzle row
             const uint32_t acc = (!first_kb || k > 0) ? 1u : 0u;
+#ifdef DAMC_TC_ISSUE_LANE0
             if (F32) {
               if (CG == 2) umma_tf32_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
               else umma_tf32(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
@@ -501,14 +508,25 @@ convgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (CG == 2) umma_bf16_2sm(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
               else umma_bf16(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
             }
+#else
+            umma_elect<F32, CG>(d_blk, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, acc);
+#endif
           }
+#ifdef DAMC_TC_ISSUE_LANE0
           if (CG == 2) umma_commit_2sm(bar_empty(stage)); else umma_commit(bar_empty(stage));  // frees the smem slot
+#else
+          umma_commit_elect<CG>(bar_empty(stage));  // frees the smem slot
+#endif
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
         if (kb1 <= kb0) {  // empty K range (trailing split): nothing was accumulated -> signal with zeros impossible;
           // the host guarantees kb_per_split * (ksplit-1) < kb_total, so this cannot happen
         }
+#ifdef DAMC_TC_ISSUE_LANE0
         if (CG == 2) umma_commit_2sm(bar_tfull(as)); else umma_commit(bar_tfull(as));  // accumulator complete
+#else
+        umma_commit_elect<CG>(bar_tfull(as));  // accumulator complete
+#endif
       }
     }
   } else {

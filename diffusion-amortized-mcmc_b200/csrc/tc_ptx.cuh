@@ -195,6 +195,38 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// ---- issue by ONE elected lane of a CONVERGED warp -------------------------------------------------------------------
+// Inside `if (lane == 0)` the compiler wraps every tcgen05.mma / tcgen05.commit (uniform-datapath operands) into an
+// elect-and-retry loop and re-materialises its uniform registers; when the whole warp runs the issue loop and the election
+// happens inside the asm statement, a k-block costs the issuing warp about half the instructions.
+#define DAMC_UMMA_ELECT(KIND, GROUP)                                                                       \
+  asm volatile(                                                                                            \
+      "{\n\t.reg .pred pe, pa;\n\t"                                                                        \
+      "elect.sync _|pe, 0xffffffff;\n\t"                                                                   \
+      "setp.ne.b32 pa, %4, 0;\n\t"                                                                         \
+      "@pe tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], %1, %2, %3, pa;\n\t}"                     \
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory")
+template <bool F32, int CG>
+__device__ __forceinline__ void umma_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (F32) { if (CG == 2) DAMC_UMMA_ELECT("tf32", "2"); else DAMC_UMMA_ELECT("tf32", "1"); }
+  else { if (CG == 2) DAMC_UMMA_ELECT("f16", "2"); else DAMC_UMMA_ELECT("f16", "1"); }
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  if (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major SWIZZLE_128B: 8-row groups of 128-byte rows, 1024 B apart (SBO); LBO unused.
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   uint64_t d = 0;
