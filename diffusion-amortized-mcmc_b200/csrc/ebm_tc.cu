@@ -158,7 +158,7 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp runs the issue loop (converged); one elected lane issues (umma_elect, tc_ptx.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < a.K; ++it)
@@ -172,12 +172,12 @@ ebm_tc_step_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           const uint64_t adesc = make_sdesc(abuf + (uint32_t)kb * ET_TILE), bdesc = make_sdesc(ring + (uint32_t)stage * ET_WSTAGE);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g == 3 ? a.idesc_z : a.idesc_h,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar_wempty(stage));
+            umma_elect<false, 1>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g == 3 ? a.idesc_z : a.idesc_h,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_elect<1>(bar_wempty(stage));
           if (++stage == ET_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_acc);
+        umma_commit_elect<1>(bar_acc);
       }
     }
   } else {
