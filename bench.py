@@ -263,6 +263,9 @@ def run_ours(args):
                 eager[f"chains_{eb}"] = {"value": ev, "unit": "chain-steps/s", "ms_per_call": ems}
             eager["what"] = ("reference algorithm (oracle port of src/MCMC.py:48-74) in eager PyTorch on this B200, torch "
                              "defaults (cudnn TF32 convolutions, 4 .item() syncs per Langevin step), K=%d" % L_STEPS)
+        secondary = None
+        if world == 1 and not args.no_secondary:
+            secondary = damc_secondary(dev)
         # DRAM traffic needs ncu counters; bench.py cannot measure it live.  The figure of the newest committed ncu capture
         # of this workload is quoted and labelled with its file; null when there is none for this precision / batch.
         traffic, traffic_note = None, "not measured in this run (needs ncu); no committed capture for this precision/batch"
@@ -304,6 +307,7 @@ def run_ours(args):
                                    "event time; frac_step = the same FLOPs / whole-step time of the hook-free timed region"
                                    % (gemm_n.value, prof_steps, 100.0 * gemm_ms.value / prof_ms)},
             "eager_gpu_baseline": eager,
+            "secondary": secondary,
             "cpu_baseline": None if cpu_v is None else {
                 "value": cpu_v, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"{args.cpu_chains} chains x {args.cpu_lsteps} Langevin steps, {cpu_dt:.1f} s "
@@ -312,6 +316,38 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def damc_secondary(dev):
+    """The other sampler of the path, reported next to the headline (never part of it): the DAMC reverse loop
+    (reference workspace/src/diffusion_net.py:597-620; T = 100, xemb and z_T resident, Philox noise, fp16 operands) on the
+    hoisted-context schedule (csrc/denoiser_seq.cu), CUDA-event timed.  Any failure is reported, not raised."""
+    try:
+        import torch
+        from damc_b200 import MCMC, diffusion_net as dn
+        torch.manual_seed(1)
+        T = 100
+        Q = dn._netQ_U(nc=NC, nz=NZ, nxemb=1024, ntemb=128, nif=64, diffusion_residual=True, n_interval=T, logsnr_min=-5.1,
+                       logsnr_max=9.8, var_type="large", with_noise=True, dataset="cifar10").to(dev).eval()
+        out = {"what": "DAMC sampler loop, T = 100 reverse steps, fp16 operands, xemb / z_T resident; 2.949 MFLOP per chain and step"}
+        for Bq in (128, 16384):
+            xemb = torch.randn(Bq, 1024, device=dev) * 0.5
+            zT = torch.randn(Bq, NZ, device=dev)
+            run = lambda: MCMC.damc_sample(Q, xemb=xemb, z_init=zT, seed=5, precision="fp16")
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                run()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / 3
+            out[f"chains_{Bq}"] = {"ms": ms, "reverse_steps_per_s": Bq * T / ms * 1e3, "tflops": Bq * T * 2.949e6 / ms * 1e3 / 1e12}
+        return out
+    except Exception as exc:  # noqa: BLE001 -- the headline line must not depend on this leg
+        return {"error": repr(exc)}
 
 
 def main():
@@ -328,6 +364,7 @@ def main():
     ap.add_argument("--cpu-lsteps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the DAMC sampler timings reported under 'secondary'")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
