@@ -294,15 +294,22 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
           const uint32_t d_tmem = tmem_base + as * 256u;
           const uint32_t idesc = T.kind == SQ_EMB ? P.idesc_e : (PAIR ? (P.idesc_l & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24) : P.idesc_l);
           const uint32_t cbase = MODE == 1 ? 4u * (lcnt & 1u) : 0u;
-          const int per = T.kind == SQ_EMB ? 4 : 1;
-          for (int kb = 0; kb < T.nkb; kb += per) {
-            const int nsub = min(per, T.nkb - kb);
-            const int wc = T.k[kb].wait;
-            if (wc == SQ_W_H0) { mbar_wait(bar_hready(0), hph[0]); hph[0] ^= 1u; }
-            else if (wc == SQ_W_H1) { mbar_wait(bar_hready(1), hph[1]); hph[1] ^= 1u; }
-            else if (wc == SQ_W_STG) { mbar_wait(bar_stg, stgph); stgph ^= 1u; }
-            else if (wc == SQ_W_C) { mbar_wait(bar_cready(lcnt & 1u), (lcnt >> 1) & 1u); }
-            if (MODE == 0) {
+          // this warp's instruction stream paces the MMA-bound stretches: the tile's fields are read once, a k-block reads ONE
+          // 32-bit word of the program, and the rare branches (waits, skip stores) sit behind a single test each
+          const int nkb = T.nkb, per = T.kind == SQ_EMB ? 4 : 1, xcommit = T.xcommit;
+          const int stkb0 = T.st[0].kb, stkb1 = T.st[1].kb;
+          const uint32_t wrows128 = (uint32_t)T.wrows * 128u;
+          for (int kb = 0; kb < nkb; kb += per) {
+            const int nsub = min(per, nkb - kb);
+            const uint32_t kw = *reinterpret_cast<const uint32_t*>(&T.k[kb]);   // {ablk, wait, wcol}
+            const int wc = (int)((kw >> 8) & 0xffu);
+            if (wc) {
+              if (wc == SQ_W_H0) { mbar_wait(bar_hready(0), hph[0]); hph[0] ^= 1u; }
+              else if (wc == SQ_W_H1) { mbar_wait(bar_hready(1), hph[1]); hph[1] ^= 1u; }
+              else if (wc == SQ_W_STG) { mbar_wait(bar_stg, stgph); stgph ^= 1u; }
+              else if (wc == SQ_W_C) { mbar_wait(bar_cready(lcnt & 1u), (lcnt >> 1) & 1u); }
+            }
+            if (MODE == 0 && (kb == stkb0 || kb == stkb1)) {
 #pragma unroll
               for (int q = 0; q < 2; ++q)
                 if (T.st[q].kb == kb && lane == 0) {
@@ -316,14 +323,15 @@ __global__ void __launch_bounds__(MODE == 0 ? SQ_THREADS : SQ_THREADS_GATE, 1) d
             tc_fence_after();
             if (lg && kb == 0) P.tlog[10 * ti + 3] = sq_now();
             for (int j = 0; j < nsub; ++j) {
-              const uint64_t adesc = make_sdesc(blocks + (cbase + T.k[kb + j].ablk) * SQ_BLK);
-              const uint64_t bdesc = make_sdesc(ring + (uint32_t)stage * WST + (uint32_t)j * T.wrows * 128u);
+              const uint32_t ablk = j == 0 ? (kw & 0xffu) : (uint32_t)T.k[kb + j].ablk;
+              const uint64_t adesc = make_sdesc(blocks + (cbase + ablk) * SQ_BLK);
+              const uint64_t bdesc = make_sdesc(ring + (uint32_t)stage * WST + (uint32_t)j * wrows128);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 sq_umma<PAIR>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
             }
             sq_commit<PAIR>(bar_wempty(stage));
-            if (T.xcommit && T.xcommit == kb + nsub) sq_commit<PAIR>(bar_xfree);
+            if (xcommit && xcommit == kb + nsub) sq_commit<PAIR>(bar_xfree);
             if (++stage == SQ_STAGES) { stage = 0; phase ^= 1u; }
           }
           if (MODE == 0 && lane == 0) {   // (the stores were issued microseconds ago: these waits do not stall)
